@@ -1,0 +1,291 @@
+// classify.cu -- K0: boundary classification (integer work, bit-exact).
+//
+// Replaces SimulationGrid::rebuild_boundary_list / neighbors / calculate_edges
+// (/root/reference/src/grid/mod.rs:167-235, 270-332):
+//   * every non-Fluid cell goes on the boundary list, sorted x-major
+//     (BTreeSet<BoundaryIndex>, src/types.rs:18-19) == increasing linear index,
+//   * fluid_cells counts Fluid cells anywhere in the array,
+//   * the 4-bit "neighbour is Fluid" mask (W, E, N, S; out of grid = not fluid)
+//     selects the edge class; any other mask is BoundaryTooThinError and the
+//     FIRST offender in x-major order is the one reported.
+#include "sb_internal.cuh"
+
+namespace sb {
+
+namespace {
+
+constexpr int CL_THREADS = 256;
+constexpr int CL_ITEMS = 4;
+constexpr int CL_CHUNK = CL_THREADS * CL_ITEMS;
+
+// mask bits: W=8, E=4, N=2, S=1 -> edge class (0xFF = too thin); src/grid/mod.rs:297-331
+__constant__ uint8_t c_edge_of_mask[16] = {
+    SB_EDGE_NONE, SB_EDGE_S, SB_EDGE_N, 0xFF,        // 0000 0001 0010 0011
+    SB_EDGE_E,    SB_EDGE_SE, SB_EDGE_NE, 0xFF,      // 0100 0101 0110 0111
+    SB_EDGE_W,    SB_EDGE_SW, SB_EDGE_NW, 0xFF,      // 1000 1001 1010 1011
+    0xFF,         0xFF,       0xFF,       0xFF};     // 11xx
+
+__global__ void edge_kernel(uint8_t *__restrict__ cflag, Geom g,
+                            unsigned long long *__restrict__ err,
+                            unsigned long long *__restrict__ fluid_owned) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = g.nxl * g.NY;
+    unsigned long long fluid = 0;
+    if (i < total) {
+        int64_t lx = i / g.NY, y = i - lx * g.NY;
+        int64_t c = lx * g.pitch + y;
+        uint8_t fl = cflag[c];
+        if (fl & CF_VALID) {
+            int kind = cf_kind(fl);
+            if (kind == SB_KIND_FLUID) {
+                if (lx >= g.own0 && lx < g.own1) fluid = 1;
+            } else {
+                // neighbour bytes may be rewritten concurrently, but only their edge
+                // bits change; kind and valid bits are stable
+                bool w = lx > 0 && cf_is_fluid(cflag[c - g.pitch] & 0x87);
+                bool e = lx + 1 < g.nxl && cf_is_fluid(cflag[c + g.pitch] & 0x87);
+                bool n = y > 0 && cf_is_fluid(cflag[c - 1] & 0x87);
+                bool s = y + 1 < g.NY && cf_is_fluid(cflag[c + 1] & 0x87);
+                int m = (w << 3) | (e << 2) | (n << 1) | (int)s;
+                uint8_t edge = c_edge_of_mask[m];
+                if (edge == 0xFF) {
+                    // rows whose x-neighbours lie outside this slab cannot be judged here
+                    bool judged = (lx > 0 || g.gx0 + lx == 0) &&
+                                  (lx + 1 < g.nxl || g.gx0 + lx == g.NX - 1);
+                    if (judged && lx >= g.own0 && lx < g.own1)
+                        atomicMin(err, (unsigned long long)((g.gx0 + lx) * g.NY + y));
+                    edge = 0;
+                }
+                cflag[c] = (uint8_t)(CF_VALID | kind | (edge << 3));
+            }
+        }
+    }
+    // block-level count of owned fluid cells -> one atomic per block
+    __shared__ unsigned long long sh[CL_THREADS / 32];
+    for (int o = 16; o; o >>= 1) fluid += __shfl_down_sync(0xffffffffu, fluid, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = fluid;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int k = 0; k < CL_THREADS / 32; k++) t += sh[k];
+        if (t) atomicAdd(fluid_owned, t);
+    }
+}
+
+__device__ __forceinline__ bool is_listed(const uint8_t *cflag, const Geom &g, int64_t i) {
+    if (i >= g.nxl * g.NY) return false;
+    int64_t lx = i / g.NY, y = i - lx * g.NY;
+    return cf_is_boundary(cflag[lx * g.pitch + y]);
+}
+
+// per-chunk count of boundary cells
+__global__ void count_kernel(const uint8_t *__restrict__ cflag, Geom g,
+                             int64_t *__restrict__ counts) {
+    int64_t base = (int64_t)blockIdx.x * CL_CHUNK + (int64_t)threadIdx.x * CL_ITEMS;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < CL_ITEMS; k++) c += is_listed(cflag, g, base + k);
+    __shared__ int sh[CL_THREADS / 32];
+    for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < CL_THREADS / 32; k++) t += sh[k];
+        counts[blockIdx.x] = t;
+    }
+}
+
+// single-block exclusive scan of counts[0..n); counts[n] receives the total
+__global__ void scan_kernel(int64_t *__restrict__ counts, int64_t n) {
+    __shared__ int64_t warp_sums[32];
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += blockDim.x) {
+        int64_t i = base + threadIdx.x;
+        int64_t v = i < n ? counts[i] : 0;
+        int64_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int nw = blockDim.x >> 5;
+            int64_t w = threadIdx.x < nw ? warp_sums[threadIdx.x] : 0;
+            int64_t wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                int64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if ((int)threadIdx.x >= o) wi += t;
+            }
+            warp_sums[threadIdx.x] = wi - w;  // exclusive prefix of the warp sums
+        }
+        __syncthreads();
+        int64_t excl = carry + warp_sums[threadIdx.x >> 5] + incl - v;
+        if (i < n) counts[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[n] = carry;
+}
+
+// write list entries in index order
+__global__ void fill_kernel(const uint8_t *__restrict__ cflag, Geom g,
+                            const int64_t *__restrict__ offsets, int64_t *__restrict__ lin,
+                            uint8_t *__restrict__ ke, double *__restrict__ bu,
+                            double *__restrict__ bv) {
+    int64_t base = (int64_t)blockIdx.x * CL_CHUNK + (int64_t)threadIdx.x * CL_ITEMS;
+    bool flag[CL_ITEMS];
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < CL_ITEMS; k++) {
+        flag[k] = is_listed(cflag, g, base + k);
+        c += flag[k];
+    }
+    int incl = c;
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    __shared__ int warp_sums[CL_THREADS / 32];
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int k = 0; k < (int)(threadIdx.x >> 5); k++) woff += warp_sums[k];
+    int64_t pos = offsets[blockIdx.x] + woff + incl - c;
+#pragma unroll
+    for (int k = 0; k < CL_ITEMS; k++) {
+        if (flag[k]) {
+            int64_t i = base + k;
+            int64_t lx = i / g.NY, y = i - lx * g.NY;
+            int64_t cidx = lx * g.pitch + y;
+            uint8_t fl = cflag[cidx];
+            lin[pos] = cidx;
+            ke[pos] = (uint8_t)(cf_kind(fl) | (cf_edge(fl) << 3));
+            bu[pos] = 0.0;
+            bv[pos] = 0.0;
+            pos++;
+        }
+    }
+}
+
+// scatter the host's sparse velocity table into the list (binary search by index)
+__global__ void velocity_kernel(const sb_boundary_velocity *__restrict__ tab, size_t ntab,
+                                Geom g, const int64_t *__restrict__ lin,
+                                const uint8_t *__restrict__ ke, uint64_t n,
+                                double *__restrict__ bu, double *__restrict__ bv) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntab) return;
+    int64_t lx = (int64_t)tab[t].x - g.gx0;
+    if (lx < 0 || lx >= g.nxl || (int64_t)tab[t].y >= g.NY) return;
+    int64_t key = lx * g.pitch + (int64_t)tab[t].y;
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (lin[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    if (lo < n && lin[lo] == key) {
+        int kind = ke[lo] & 7;
+        if (kind == SB_KIND_INFLOW || kind == SB_KIND_MOVING_WALL) {
+            bu[lo] = tab[t].u;
+            bv[lo] = tab[t].v;
+        }
+    }
+}
+
+template <typename T>
+sb_status ensure(T *&ptr, size_t &cap, size_t need) {
+    if (need <= cap) return SB_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    size_t ncap = need + need / 4 + 64;
+    SB_CUDA(cudaMalloc(&ptr, ncap * sizeof(T)));
+    cap = ncap;
+    return SB_OK;
+}
+
+void free_list(BList &b) {
+    cudaFree(b.lin); cudaFree(b.ke); cudaFree(b.bu); cudaFree(b.bv); cudaFree(b.ru);
+    cudaFree(b.rv); cudaFree(b.nu); cudaFree(b.nv); cudaFree(b.wu); cudaFree(b.wv);
+    b = BList();
+}
+
+sb_status alloc_list(BList &b, uint64_t n) {
+    uint64_t cap = n + 16;
+    SB_CUDA(cudaMalloc(&b.lin, cap * sizeof(int64_t)));
+    SB_CUDA(cudaMalloc(&b.ke, cap));
+    double **arrs[] = {&b.bu, &b.bv, &b.ru, &b.rv, &b.nu, &b.nv, &b.wu, &b.wv};
+    for (double **a : arrs) SB_CUDA(cudaMalloc(a, cap * sizeof(double)));
+    b.n = n;
+    b.cap = cap;
+    return SB_OK;
+}
+
+}  // namespace
+
+// Classify all local cells, rebuild the list.  On SB_BOUNDARY_TOO_THIN the previous
+// list and fluid count stay in force (src/grid/mod.rs:232-233); the edge bits of
+// cflag are then those of the FAILED scan, exactly like the reference's Display-only
+// BTreeSet, and get rewritten by the caller's rollback + re-classification.
+sb_status classify(sb_sim *s) {
+    const Geom &g = s->g;
+    int64_t total = g.nxl * g.NY;
+    unsigned long long init[2] = {~0ull, 0ull};
+    SB_CUDA(cudaMemcpyAsync(s->d_err, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
+    int nb_edge = (int)((total + CL_THREADS - 1) / CL_THREADS);
+    edge_kernel<<<nb_edge, CL_THREADS, 0, s->stream>>>(s->cflag, g, s->d_err, s->d_err + 1);
+    s->launches++;
+    unsigned long long res[2];
+    SB_CUDA(cudaMemcpyAsync(res, s->d_err, sizeof(res), cudaMemcpyDeviceToHost, s->stream));
+    SB_CUDA(cudaStreamSynchronize(s->stream));
+    if (res[0] != ~0ull) {
+        s->err_xy[0] = res[0] / (unsigned long long)g.NY;
+        s->err_xy[1] = res[0] % (unsigned long long)g.NY;
+        uint8_t fl = 0;
+        int64_t c = ((int64_t)s->err_xy[0] - g.gx0) * g.pitch + (int64_t)s->err_xy[1];
+        SB_CUDA(cudaMemcpy(&fl, s->cflag + c, 1, cudaMemcpyDeviceToHost));
+        s->err_kind = (uint8_t)cf_kind(fl);
+        set_error("BoundaryTooThinError: cell has fluid on opposing sides");
+        return SB_BOUNDARY_TOO_THIN;
+    }
+    int64_t nchunks = (total + CL_CHUNK - 1) / CL_CHUNK;
+    sb_status st = ensure(s->d_scan, s->scan_cap, (size_t)nchunks + 1);
+    if (st) return st;
+    count_kernel<<<(int)nchunks, CL_THREADS, 0, s->stream>>>(s->cflag, g, s->d_scan);
+    scan_kernel<<<1, 1024, 0, s->stream>>>(s->d_scan, nchunks);
+    s->launches += 2;
+    int64_t nlist = 0;
+    SB_CUDA(cudaMemcpyAsync(&nlist, s->d_scan + nchunks, sizeof(int64_t), cudaMemcpyDeviceToHost,
+                            s->stream));
+    SB_CUDA(cudaStreamSynchronize(s->stream));
+    free_list(s->bl);
+    st = alloc_list(s->bl, (uint64_t)nlist);
+    if (st) return st;
+    fill_kernel<<<(int)nchunks, CL_THREADS, 0, s->stream>>>(s->cflag, g, s->d_scan, s->bl.lin,
+                                                            s->bl.ke, s->bl.bu, s->bl.bv);
+    s->launches++;
+    SB_CUDA(cudaGetLastError());
+    s->fluid_cells = (double)res[1];  // owned fluid cells; slab mode sums over ranks later
+    return apply_velocity_table(s);
+}
+
+sb_status apply_velocity_table(sb_sim *s) {
+    size_t n = s->velocities.size();
+    if (n == 0 || s->bl.n == 0) return SB_OK;
+    sb_boundary_velocity *d_tab = nullptr;
+    SB_CUDA(cudaMalloc(&d_tab, n * sizeof(sb_boundary_velocity)));
+    SB_CUDA(cudaMemcpyAsync(d_tab, s->velocities.data(), n * sizeof(sb_boundary_velocity),
+                            cudaMemcpyHostToDevice, s->stream));
+    velocity_kernel<<<(int)((n + 255) / 256), 256, 0, s->stream>>>(
+        d_tab, n, s->g, s->bl.lin, s->bl.ke, s->bl.n, s->bl.bu, s->bl.bv);
+    s->launches++;
+    SB_CUDA(cudaStreamSynchronize(s->stream));
+    SB_CUDA(cudaFree(d_tab));
+    return SB_OK;
+}
+
+}  // namespace sb

@@ -1,0 +1,160 @@
+// sb_internal.cuh -- shared definitions of the stroemung_b200 CUDA library.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/stroemung_b200.h"
+
+namespace sb {
+
+// ---- per-cell flag byte (device representation of Cell + Option<EdgeType>) -----
+// bits 0-2 kind (sb_kind), bits 3-6 edge (sb_edge), bit 7 = cell exists.
+// 0x00 therefore means "outside the grid" -- what TMA's out-of-bounds zero fill and
+// unowned slab rows produce -- and such cells are inert everywhere.
+constexpr uint8_t CF_VALID = 0x80;
+constexpr uint8_t CF_FLUID = CF_VALID | SB_KIND_FLUID;
+__host__ __device__ __forceinline__ int cf_kind(uint8_t f) { return f & 7; }
+__host__ __device__ __forceinline__ int cf_edge(uint8_t f) { return (f >> 3) & 15; }
+__host__ __device__ __forceinline__ bool cf_is_fluid(uint8_t f) { return f == CF_FLUID; }
+// a boundary cell of the grid (present and not fluid)
+__host__ __device__ __forceinline__ bool cf_is_boundary(uint8_t f) {
+    return (f & CF_VALID) && (f & 7) != SB_KIND_FLUID;
+}
+
+// geometry of one slab (single GPU: the whole grid), passed by value to kernels
+struct Geom {
+    int64_t NX, NY;   // global grid size
+    int64_t nxl;      // local rows (owned + 2*halo)
+    int64_t pitch;    // elements per row (multiple of 16)
+    int64_t gx0;      // global x of local row 0 (may be negative in slab mode)
+    int64_t own0, own1;  // owned local rows [own0, own1)
+};
+
+// boundary list (BoundaryList, src/grid/mod.rs:61-69) as device SoA, x-major sorted
+struct BList {
+    uint64_t n = 0, cap = 0;
+    int64_t *lin = nullptr;  // local linear index lx*pitch + y
+    uint8_t *ke = nullptr;   // kind | edge << 3
+    double *bu = nullptr, *bv = nullptr;     // Inflow / MovingWall velocity
+    double *ru = nullptr, *rv = nullptr;     // values u[b], v[b] take after set_u_and_v (u_v_restore)
+    double *nu = nullptr, *nv = nullptr;     // scratch: new u[b], v[b] of the BC gather
+    double *wu = nullptr, *wv = nullptr;     // scratch: values for u[west nbr], v[north nbr]
+};
+
+struct SorCtl {        // device-resident control block of one SOR solve
+    int32_t active_T;  // sweeps the next pass performs (0 = solve finished / idle)
+    int32_t src;       // index of the current pressure buffer
+    uint32_t iters_done;
+    uint32_t max_iterations;
+    int32_t block_T;   // configured temporal block
+    int32_t cap_hit;   // finished by reaching max_iterations
+    int32_t finished;
+    int32_t pad;
+    double last_norm;
+    double norms[8];   // norms of the last pass (diagnostics / sb_sor_sweeps)
+};
+
+#define SB_CUDA(call)                                                               \
+    do {                                                                            \
+        cudaError_t _e = (call);                                                    \
+        if (_e != cudaSuccess) {                                                    \
+            sb::set_error(std::string(#call) + ": " + cudaGetErrorString(_e));     \
+            return SB_CUDA_ERROR;                                                   \
+        }                                                                           \
+    } while (0)
+
+void set_error(const std::string &msg);
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+}  // namespace sb
+
+// the opaque handle of the C ABI
+struct sb_sim {
+    sb_params prm;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    sb::Geom g{};
+    int halo = 0;
+    // fields; p is double-buffered for the red-black passes
+    double *p[2] = {nullptr, nullptr};
+    int cur = 0;
+    double *u = nullptr, *v = nullptr, *f = nullptr, *gq = nullptr, *rhs = nullptr;
+    uint8_t *cflag = nullptr;
+    size_t field_bytes = 0, flag_bytes = 0;
+    sb::BList bl;
+    // sparse velocity table as given by the host (global coordinates)
+    std::vector<sb_boundary_velocity> velocities;
+    double fluid_cells = 0.0;
+    // reductions / control
+    double *d_partial = nullptr;  // per-block partial sums
+    size_t partial_cap = 0;
+    double *d_scalars = nullptr;  // small device scratch (results of final reductions)
+    double *h_scalars = nullptr;  // pinned mirror
+    sb::SorCtl *d_ctl = nullptr, *h_ctl = nullptr;
+    int32_t *d_lex_sync = nullptr;  // wavefront kernel: ticket + per-band progress
+    size_t lex_sync_cap = 0;
+    // classification scratch
+    int64_t *d_scan = nullptr;
+    size_t scan_cap = 0;
+    unsigned long long *d_err = nullptr;  // first too-thin cell (min linear global index)
+    // bookkeeping mirrored from the reference's structs
+    double time = 0.0;
+    uint32_t iterations = 0;
+    int has_initial_norm = 0;
+    double initial_norm_squared = 0.0;
+    double pressure_range[2] = {0, 0}, speed_range[2] = {0, 0};
+    double umax = 0.0, vmax = 0.0;  // max |u|, |v| over fluid cells (adaptive delt)
+    uint32_t last_sor_iterations = 0;
+    double last_norm_squared = 0.0;
+    uint32_t sor_batch_hint = 0;
+    uint64_t err_xy[2] = {0, 0};
+    uint8_t err_kind = 0;
+    uint64_t launches = 0;
+    cudaEvent_t ev_sor0 = nullptr, ev_sor1 = nullptr;
+    double last_sor_ms = 0.0;
+    // tensor maps for the red-black pass (built lazily per buffer)
+    bool tmaps_ready = false;
+    CUtensorMap tm_p[2], tm_rhs, tm_flag;
+};
+
+namespace sb {
+
+// ---- kernels' host launchers (defined in the .cu files) ------------------------
+// classify.cu
+sb_status classify(sb_sim *s);                 // cflag edges + list + fluid count
+sb_status apply_velocity_table(sb_sim *s);     // scatter sparse (x,y,u,v) into the list
+// stages.cu
+sb_status launch_velocity_bc(sb_sim *s);
+sb_status launch_fg(sb_sim *s);
+sb_status launch_rhs(sb_sim *s);
+sb_status launch_pressure_bc(sb_sim *s, int guarded);
+sb_status launch_norm_partials(sb_sim *s, int guarded, int *nblocks);
+sb_status launch_adapt_uv(sb_sim *s);
+sb_status launch_pressure_range(sb_sim *s);
+sb_status launch_speed_range(sb_sim *s);
+sb_status launch_cellop(int op, const double *u9, const double *v9, const double *scal,
+                        double *out);
+// sor_lex.cu
+sb_status launch_sor_lex_sweep(sb_sim *s, int guarded);
+// sor_rb.cu
+sb_status launch_sor_rb_pass(sb_sim *s, int *ntiles, int norm_only);
+int rb_halo_rows(int T);
+// finalize (stages.cu): sum partials, exit test, update ctl
+sb_status launch_sor_finalize(sb_sim *s, int nparts, double initial_norm, double eps2,
+                              int test_exit, double *norm_hist);
+// d_scalars[0] = (sum of partial[0..n)) / fluid_cells, read back into *out
+sb_status reduce_norm(sb_sim *s, int nparts, double *out);
+sb_status restore_edges_from_list(sb_sim *s);
+sb_status launch_mark_valid(sb_sim *s, const uint8_t *d_kind_rows, int keep_edges);
+sb_status launch_preset(sb_sim *s, int preset, const double *args);
+sb_status launch_edit_block(sb_sim *s, int64_t gx, int64_t gy, uint8_t kind, double *backup,
+                            int restore, int32_t *modified);
+
+}  // namespace sb

@@ -1,0 +1,688 @@
+// stages.cu -- every per-tick stage except the SOR sweeps, strict IEEE f64.
+//
+//   K1 velocity BC      SimulationGrid::set_boundary_u_and_v   src/grid/mod.rs:414-651
+//   K2 F, G             Simulation::calculate_f_and_g          src/simulation.rs:122-202
+//      RHS              Simulation::calculate_rhs              src/simulation.rs:204-214
+//   K3 pressure BC      copy_pressure_to_boundaries            src/grid/mod.rs:343-412
+//   K5 residual norm    calculate_norm_squared / residual      src/simulation.rs:216-227
+//   K6 velocity update  Simulation::set_u_and_v                src/simulation.rs:287-322
+//   K7 ranges           calculate_{pressure,speed}_range       src/grid/mod.rs:237-268
+// (paths relative to /root/reference).  Compiled with -fmad=false so that no a*b+c
+// is contracted; see cellops.cuh for the operator restatements.
+#include "cellops.cuh"
+#include "sb_internal.cuh"
+
+#include <float.h>
+
+namespace sb {
+
+namespace {
+
+constexpr int TPB = 256;
+
+// ---- block reductions ---------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+    for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- K1: velocity boundary conditions ------------------------------------------------
+// The reference pass is sequential and in place.  Restated as a gather:
+// every read sees the pre-pass value, except v[west_neighbor] (edges W, NW), which the
+// boundary cell (bx-1, by+1) -- earlier in x-major order -- may already have overwritten
+// through its own north neighbour: NoSlip -> 0.0, Inflow/MovingWall -> its v, else unchanged.
+// Phase 1 (this kernel) gathers into list scratch, phase 2 scatters; two launches make the
+// "pre-pass" reads race-free.
+__global__ void velocity_bc_gather(Geom g, const double *__restrict__ u,
+                                   const double *__restrict__ v,
+                                   const uint8_t *__restrict__ cflag, BList bl, int64_t row0,
+                                   int64_t row1) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= bl.n) return;
+    int64_t b = bl.lin[k];
+    int64_t lx = b / g.pitch;
+    int kind = bl.ke[k] & 7, edge = bl.ke[k] >> 3;
+    double ub = u[b], vb = v[b];
+    double nu = ub, nv = vb;         // new u[b], v[b]
+    double wu = 0.0, wv = 0.0;       // values for u[w], v[n] (when written)
+    double ru = ub, rv = vb;         // what set_u_and_v's restore leaves in u[b], v[b]
+    if (edge != SB_EDGE_NONE && lx >= row0 && lx < row1) {
+        int64_t n = b - 1, so = b + 1, ea = b + g.pitch, w = b - g.pitch;
+        bool has_n = edge == SB_EDGE_N || edge == SB_EDGE_NE || edge == SB_EDGE_NW;
+        bool has_e = edge == SB_EDGE_NE || edge == SB_EDGE_E || edge == SB_EDGE_SE;
+        bool has_s = edge == SB_EDGE_SE || edge == SB_EDGE_S || edge == SB_EDGE_SW;
+        bool has_w = edge == SB_EDGE_SW || edge == SB_EDGE_W || edge == SB_EDGE_NW;
+        double u_n = has_n ? u[n] : 0.0, v_n = has_n ? v[n] : 0.0;
+        double u_e = has_e ? u[ea] : 0.0, v_e = has_e ? v[ea] : 0.0;
+        double u_s = has_s ? u[so] : 0.0, v_s = has_s ? v[so] : 0.0;
+        double u_w = has_w ? u[w] : 0.0, v_w = has_w ? v[w] : 0.0;
+        if (has_w && (edge == SB_EDGE_W || edge == SB_EDGE_NW)) {
+            // the one read-after-write of the sequential pass: cell (bx-1, by+1)
+            int64_t by = b - lx * g.pitch;
+            uint8_t fl = by + 1 < g.NY ? cflag[w + 1] : (uint8_t)0;
+            int k2 = cf_kind(fl);
+            if ((fl & CF_VALID) && k2 != SB_KIND_FLUID && k2 != SB_KIND_OUTFLOW) {
+                // its edge contains North (w is fluid), so it writes v[w] = its boundary_v
+                if (k2 == SB_KIND_NOSLIP) v_w = 0.0;
+                else {
+                    // Inflow / MovingWall: look its velocity up in the list
+                    int64_t key = w + 1;
+                    uint64_t lo = 0, hi = bl.n;
+                    while (lo < hi) {
+                        uint64_t mid = (lo + hi) >> 1;
+                        if (bl.lin[mid] < key) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    v_w = bl.bv[lo];
+                }
+            }
+        }
+        if (kind == SB_KIND_OUTFLOW) {
+            // src/grid/mod.rs:489-536
+            switch (edge) {
+            case SB_EDGE_N: nu = u_n; nv = v_n; break;
+            case SB_EDGE_NE: nu = u_n; nv = v_e; break;
+            case SB_EDGE_E: nu = u_e; nv = v_e; break;
+            case SB_EDGE_SE: nu = u_e; nv = v_s; break;
+            case SB_EDGE_S: nu = u_s; nv = v_s; break;
+            case SB_EDGE_SW: nu = u_w; nv = v_s; break;
+            case SB_EDGE_W: nu = u_w; nv = v_w; break;
+            case SB_EDGE_NW: nu = u_n; nv = v_w; break;
+            }
+            // second restore record holds the (unchanged) neighbour values (:602-648)
+            ru = has_w ? u_w : nu;
+            rv = has_n ? v_n : nv;
+            // mark "no neighbour writes" with NaN-free sentinel: handled in scatter by kind
+        } else {
+            double bu = 0.0, bv = 0.0;
+            if (kind != SB_KIND_NOSLIP) { bu = bl.bu[k]; bv = bl.bv[k]; }
+            if (kind == SB_KIND_MOVING_WALL) {
+                // extension: tangential ghost value reflects about the wall velocity
+                switch (edge) {
+                case SB_EDGE_N: nu = (2.0 * bu) - u_n; break;
+                case SB_EDGE_NE: nu = bu; nv = (2.0 * bv) - v_e; break;
+                case SB_EDGE_E: nu = bu; nv = (2.0 * bv) - v_e; break;
+                case SB_EDGE_SE: nu = bu; nv = bv; break;
+                case SB_EDGE_S: nu = (2.0 * bu) - u_s; nv = bv; break;
+                case SB_EDGE_SW: nu = (2.0 * bu) - u_s; nv = bv; break;
+                case SB_EDGE_W: nv = (2.0 * bv) - v_w; break;
+                case SB_EDGE_NW: nu = (2.0 * bu) - u_n; nv = (2.0 * bv) - v_w; break;
+                }
+            } else {
+                // NoSlip (:437-488) and Inflow (:537-586) share one table
+                switch (edge) {
+                case SB_EDGE_N: nu = -u_n; break;
+                case SB_EDGE_NE: nu = bu; nv = -v_e; break;
+                case SB_EDGE_E: nu = bu; nv = -v_e; break;
+                case SB_EDGE_SE: nu = bu; nv = bv; break;
+                case SB_EDGE_S: nu = -u_s; nv = bv; break;
+                case SB_EDGE_SW: nu = -u_s; nv = bv; break;
+                case SB_EDGE_W: nv = -v_w; break;
+                case SB_EDGE_NW: nu = -u_n; nv = -v_w; break;
+                }
+            }
+            wu = bu;  // u[west_neighbor] = boundary_u  (edges SW, W, NW)
+            wv = bv;  // v[north_neighbor] = boundary_v (edges N, NE, NW)
+            ru = has_w ? bu : nu;
+            rv = has_n ? bv : nv;
+        }
+    }
+    bl.nu[k] = nu; bl.nv[k] = nv; bl.wu[k] = wu; bl.wv[k] = wv;
+    bl.ru[k] = ru; bl.rv[k] = rv;
+}
+
+__global__ void velocity_bc_scatter(Geom g, double *__restrict__ u, double *__restrict__ v,
+                                    BList bl, int64_t row0, int64_t row1) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= bl.n) return;
+    int64_t b = bl.lin[k];
+    int64_t lx = b / g.pitch;
+    int kind = bl.ke[k] & 7, edge = bl.ke[k] >> 3;
+    if (edge == SB_EDGE_NONE || lx < row0 || lx >= row1) return;
+    u[b] = bl.nu[k];
+    v[b] = bl.nv[k];
+    if (kind != SB_KIND_OUTFLOW) {
+        if (edge == SB_EDGE_SW || edge == SB_EDGE_W || edge == SB_EDGE_NW) u[b - g.pitch] = bl.wu[k];
+        if (edge == SB_EDGE_N || edge == SB_EDGE_NE || edge == SB_EDGE_NW) v[b - 1] = bl.wv[k];
+    }
+}
+
+// ---- K2: F and G ------------------------------------------------------------------------
+// All interior cells get the stencil value (fluid or not); afterwards the reference
+// overwrites f[b]=u[b], g[b]=v[b] on every boundary cell and g[n]=v[n] / f[w]=u[w] on the
+// fluid cell north / west of one (src/simulation.rs:167-201).  Per cell that is:
+//   non-fluid c                       -> f = u[c], g = v[c]
+//   fluid c with (x+1, y) non-fluid   -> f = u[c]   (c is that cell's west neighbour)
+//   fluid c with (x, y+1) non-fluid   -> g = v[c]   (c is that cell's north neighbour)
+// Ring cells are outside the stencil loop: they only receive the overwrites.
+__global__ void fg_kernel(Geom g, const double *__restrict__ u, const double *__restrict__ v,
+                          const uint8_t *__restrict__ cflag, double *__restrict__ f,
+                          double *__restrict__ gq, int64_t row0, int64_t row1, double delx,
+                          double dely, double delt, double gamma, double reynolds) {
+    int64_t y = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    int64_t lx = row0 + blockIdx.x;
+    if (y >= g.NY || lx >= row1) return;
+    int64_t gx = g.gx0 + lx;
+    if (gx < 0 || gx >= g.NX) return;
+    int64_t c = lx * g.pitch + y;
+    uint8_t fl = cflag[c];
+    bool interior = gx >= 1 && gx <= g.NX - 2 && y >= 1 && y <= g.NY - 2;
+    if (!cf_is_fluid(fl)) {
+        f[c] = u[c];
+        gq[c] = v[c];
+        return;
+    }
+    bool east_solid = gx + 1 < g.NX && lx + 1 < g.nxl && !cf_is_fluid(cflag[c + g.pitch]);
+    bool south_solid = y + 1 < g.NY && !cf_is_fluid(cflag[c + 1]);
+    double fv = 0.0, gv = 0.0;
+    if (interior && !(east_solid && south_solid)) {
+        Stencil9 su, sv;
+        int64_t w = c - g.pitch, e = c + g.pitch;
+        su.nw = u[w - 1]; su.w = u[w]; su.sw = u[w + 1];
+        su.n = u[c - 1];  su.c = u[c]; su.s = u[c + 1];
+        su.ne = u[e - 1]; su.e = u[e]; su.se = u[e + 1];
+        sv.nw = v[w - 1]; sv.w = v[w]; sv.sw = v[w + 1];
+        sv.n = v[c - 1];  sv.c = v[c]; sv.s = v[c + 1];
+        sv.ne = v[e - 1]; sv.e = v[e]; sv.se = v[e + 1];
+        if (!east_solid) fv = calculate_f(su, sv, delx, dely, delt, gamma, reynolds);
+        if (!south_solid) gv = calculate_g(su, sv, delx, dely, delt, gamma, reynolds);
+    }
+    if (east_solid) f[c] = u[c];
+    else if (interior) f[c] = fv;
+    if (south_solid) gq[c] = v[c];
+    else if (interior) gq[c] = gv;
+}
+
+// ---- RHS: all cells with x >= 1 and y >= 1, fluid or not (src/simulation.rs:204-214) ----
+__global__ void rhs_kernel(Geom g, const double *__restrict__ f, const double *__restrict__ gq,
+                           double *__restrict__ rhs, int64_t row0, int64_t row1, double delx,
+                           double dely, double delt) {
+    int64_t y = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    int64_t lx = row0 + blockIdx.x;
+    if (y < 1 || y >= g.NY || lx >= row1) return;
+    int64_t gx = g.gx0 + lx;
+    if (gx < 1 || gx >= g.NX) return;
+    int64_t c = lx * g.pitch + y;
+    rhs[c] = (((f[c] - f[c - g.pitch]) / delx) + ((gq[c] - gq[c - 1]) / dely)) / delt;
+}
+
+// ---- K3: pressure BC over the boundary list (reads fluid cells, writes boundary cells) ---
+__global__ void pressure_bc_kernel(Geom g, double *const *__restrict__ pbuf,
+                                   const SorCtl *__restrict__ ctl, int guarded, BList bl) {
+    if (guarded && ctl->active_T == 0) return;
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= bl.n) return;
+    int edge = bl.ke[k] >> 3;
+    if (edge == SB_EDGE_NONE) return;
+    double *p = pbuf[ctl->src];
+    int64_t b = bl.lin[k];
+    int64_t n = b - 1, so = b + 1, ea = b + g.pitch, w = b - g.pitch;
+    switch (edge) {
+    case SB_EDGE_N: p[b] = p[n]; break;
+    case SB_EDGE_NE: p[b] = (p[n] + p[ea]) / 2.0; break;
+    case SB_EDGE_E: p[b] = p[ea]; break;
+    case SB_EDGE_SE: p[b] = (p[so] + p[ea]) / 2.0; break;
+    case SB_EDGE_S: p[b] = p[so]; break;
+    case SB_EDGE_SW: p[b] = (p[so] + p[w]) / 2.0; break;
+    case SB_EDGE_W: p[b] = p[w]; break;
+    case SB_EDGE_NW: p[b] = (p[n] + p[w]) / 2.0; break;
+    }
+}
+
+// ---- K5: residual norm, partial sums over ALL interior cells (fluid or not) ------------
+// One block per (row, 1024-column segment)-ish chunk; fixed tree inside the block, fixed
+// order in the finalize kernel => deterministic.  The reference folds sequentially in
+// row-major order; the different association is covered by the 1e-12 relative allowance.
+constexpr int NORM_ROWS_PER_BLOCK = 4;
+__global__ void norm_partial_kernel(Geom g, double *const *__restrict__ pbuf,
+                                    const SorCtl *__restrict__ ctl, int guarded,
+                                    const double *__restrict__ rhs, double *__restrict__ partial,
+                                    double delx, double dely) {
+    if (guarded && ctl->active_T == 0) return;
+    const double *p = pbuf[ctl->src];
+    double acc = 0.0;
+    int64_t lx_base = g.own0 + (int64_t)blockIdx.x * NORM_ROWS_PER_BLOCK;
+    for (int r = 0; r < NORM_ROWS_PER_BLOCK; r++) {
+        int64_t lx = lx_base + r;
+        int64_t gx = g.gx0 + lx;
+        if (lx >= g.own1 || gx < 1 || gx > g.NX - 2) continue;
+        for (int64_t y = 1 + (int64_t)blockIdx.y * blockDim.x + threadIdx.x; y <= g.NY - 2;
+             y += (int64_t)gridDim.y * blockDim.x) {
+            int64_t c = lx * g.pitch + y;
+            double rr = residual(p[c], p[c - 1], p[c + 1], p[c - g.pitch], p[c + g.pitch], delx,
+                                 dely, rhs[c]);
+            acc = acc + (rr * rr);
+        }
+    }
+    __shared__ double sh[TPB / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < TPB / 32; k++) t += sh[k];
+        partial[(int64_t)blockIdx.x * gridDim.y + blockIdx.y] = t;
+    }
+}
+
+// ---- finalize: total the partials of each level, apply the exit test, advance ctl -------
+// partial layout: [level][part].  Exit rule of src/simulation.rs:279:
+//     norm < initial_norm || norm < eps^2   -> stop after this sweep.
+// A red-black pass runs T sweeps speculatively; if the rule fires at level k < T the pass
+// is repeated from the same source buffer with T = k (deterministic, so it then ends at k).
+__global__ void sor_finalize_kernel(SorCtl *__restrict__ ctl, const double *__restrict__ partial,
+                                    int nparts, double fluid_cells, double initial_norm,
+                                    double eps2, int test_exit, double *__restrict__ norm_hist) {
+    __shared__ double sh[1024 / 32];
+    __shared__ double level_norm[8];
+    int T = ctl->active_T;
+    if (T == 0) return;
+    for (int lvl = 0; lvl < T; lvl++) {
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < nparts; i += blockDim.x)
+            acc += partial[(int64_t)lvl * nparts + i];
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += sh[k];
+            level_norm[lvl] = t / fluid_cells;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    int exit_at = 0;
+    for (int lvl = 0; lvl < T; lvl++) {
+        ctl->norms[lvl] = level_norm[lvl];
+        if (norm_hist) norm_hist[ctl->iters_done + lvl] = level_norm[lvl];
+        if (test_exit && !exit_at &&
+            ((level_norm[lvl] < initial_norm) || (level_norm[lvl] < eps2)))
+            exit_at = lvl + 1;
+    }
+    if (exit_at && exit_at < T) {
+        ctl->active_T = exit_at;  // redo this pass with fewer sweeps (same source buffer)
+        return;
+    }
+    ctl->iters_done += T;
+    ctl->src ^= (ctl->block_T > 0) ? 1 : 0;  // red-black passes ping-pong; in-place modes don't
+    ctl->last_norm = level_norm[T - 1];
+    if (exit_at) {
+        ctl->active_T = 0;
+        ctl->finished = 1;
+    } else if (ctl->iters_done >= ctl->max_iterations) {
+        ctl->active_T = 0;
+        ctl->finished = 1;
+        ctl->cap_hit = 1;
+    } else {
+        uint32_t rem = ctl->max_iterations - ctl->iters_done;
+        int next = ctl->block_T > 0 ? ctl->block_T : 1;
+        ctl->active_T = (int)(rem < (uint32_t)next ? rem : (uint32_t)next);
+    }
+}
+
+// out[0] = (sum of partial[0..n)) / fluid_cells, same tree as the finalize kernel
+__global__ void sum_partials_kernel(const double *__restrict__ partial, int nparts,
+                                    double fluid_cells, double *__restrict__ out) {
+    __shared__ double sh[1024 / 32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) acc += partial[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += sh[k];
+        out[0] = t / fluid_cells;
+    }
+}
+
+// ---- K6: velocity update + speed range + max|u|,|v| over fluid cells ----------------------
+// u, v for 0 <= x <= NX-2, 0 <= y <= NY-2, every cell (src/simulation.rs:299-311); boundary
+// cells are overwritten afterwards by the restore kernel, fluid cells are final here, so
+// the Fluid-only reductions of calculate_speed_range (src/grid/mod.rs:253-268) fuse in.
+__global__ void adapt_uv_kernel(Geom g, const double *__restrict__ p,
+                                const double *__restrict__ f, const double *__restrict__ gq,
+                                const uint8_t *__restrict__ cflag, double *__restrict__ u,
+                                double *__restrict__ v, double *__restrict__ partial,
+                                double delt, double delx, double dely) {
+    int64_t lx = g.own0 + blockIdx.x;
+    int64_t gx = g.gx0 + lx;
+    double smin = DBL_MAX, smax = 0.0, umax = 0.0, vmax = 0.0;
+    const double dtdx = delt / delx, dtdy = delt / dely;
+    if (lx < g.own1 && gx >= 0 && gx < g.NX) {
+        for (int64_t y = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; y < g.NY;
+             y += (int64_t)gridDim.y * blockDim.x) {
+            int64_t c = lx * g.pitch + y;
+            double un, vn;
+            if (gx <= g.NX - 2 && y <= g.NY - 2) {
+                double pc = p[c];
+                un = f[c] - dtdx * (p[c + g.pitch] - pc);
+                vn = gq[c] - dtdy * (p[c + 1] - pc);
+                u[c] = un;
+                v[c] = vn;
+            } else {
+                un = u[c];
+                vn = v[c];
+            }
+            if (cf_is_fluid(cflag[c])) {
+                double sq = (un * un) + (vn * vn);
+                smin = fmin(smin, sq);
+                smax = fmax(smax, sq);
+                umax = fmax(umax, fabs(un));
+                vmax = fmax(vmax, fabs(vn));
+            }
+        }
+    }
+    __shared__ double sh[4][TPB / 32];
+    smin = warp_min(smin); smax = warp_max(smax); umax = warp_max(umax); vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0) {
+        int w = threadIdx.x >> 5;
+        sh[0][w] = smin; sh[1][w] = smax; sh[2][w] = umax; sh[3][w] = vmax;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < TPB / 32; k++) {
+            smin = fmin(smin, sh[0][k]); smax = fmax(smax, sh[1][k]);
+            umax = fmax(umax, sh[2][k]); vmax = fmax(vmax, sh[3][k]);
+        }
+        int64_t blk = (int64_t)blockIdx.x * gridDim.y + blockIdx.y;
+        partial[4 * blk + 0] = smin; partial[4 * blk + 1] = smax;
+        partial[4 * blk + 2] = umax; partial[4 * blk + 3] = vmax;
+    }
+}
+
+// replay of u_v_restore (src/simulation.rs:313-320), one entry per boundary cell
+__global__ void restore_uv_kernel(Geom g, double *__restrict__ u, double *__restrict__ v,
+                                  BList bl) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= bl.n) return;
+    int64_t b = bl.lin[k];
+    int64_t lx = b / g.pitch;
+    if (lx < g.own0 || lx >= g.own1) return;
+    u[b] = bl.ru[k];
+    v[b] = bl.rv[k];
+}
+
+// min/max reductions over Fluid cells of the whole array; mode 0: p, mode 1: u^2+v^2, |u|, |v|
+__global__ void range_kernel(Geom g, const double *__restrict__ a, const double *__restrict__ b,
+                             const uint8_t *__restrict__ cflag, double *__restrict__ partial,
+                             int mode) {
+    int64_t lx = g.own0 + blockIdx.x;
+    int64_t gx = g.gx0 + lx;
+    double mn = DBL_MAX, mx = 0.0, m2 = 0.0, m3 = 0.0;
+    if (lx < g.own1 && gx >= 0 && gx < g.NX) {
+        for (int64_t y = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; y < g.NY;
+             y += (int64_t)gridDim.y * blockDim.x) {
+            int64_t c = lx * g.pitch + y;
+            if (!cf_is_fluid(cflag[c])) continue;
+            double val;
+            if (mode == 0) val = a[c];
+            else {
+                val = (a[c] * a[c]) + (b[c] * b[c]);
+                m2 = fmax(m2, fabs(a[c]));
+                m3 = fmax(m3, fabs(b[c]));
+            }
+            mn = fmin(mn, val);
+            mx = fmax(mx, val);
+        }
+    }
+    __shared__ double sh[4][TPB / 32];
+    mn = warp_min(mn); mx = warp_max(mx); m2 = warp_max(m2); m3 = warp_max(m3);
+    if ((threadIdx.x & 31) == 0) {
+        int w = threadIdx.x >> 5;
+        sh[0][w] = mn; sh[1][w] = mx; sh[2][w] = m2; sh[3][w] = m3;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < TPB / 32; k++) {
+            mn = fmin(mn, sh[0][k]); mx = fmax(mx, sh[1][k]);
+            m2 = fmax(m2, sh[2][k]); m3 = fmax(m3, sh[3][k]);
+        }
+        int64_t blk = (int64_t)blockIdx.x * gridDim.y + blockIdx.y;
+        partial[4 * blk + 0] = mn; partial[4 * blk + 1] = mx;
+        partial[4 * blk + 2] = m2; partial[4 * blk + 3] = m3;
+    }
+}
+
+// final min/max/max/max over block partials -> out[0..3] (f64::MAX, 0.0 fold seeds)
+__global__ void range_final_kernel(const double *__restrict__ partial, int64_t nblk,
+                                   double *__restrict__ out) {
+    double mn = DBL_MAX, mx = 0.0, m2 = 0.0, m3 = 0.0;
+    for (int64_t i = threadIdx.x; i < nblk; i += blockDim.x) {
+        mn = fmin(mn, partial[4 * i + 0]); mx = fmax(mx, partial[4 * i + 1]);
+        m2 = fmax(m2, partial[4 * i + 2]); m3 = fmax(m3, partial[4 * i + 3]);
+    }
+    __shared__ double sh[4][1024 / 32];
+    mn = warp_min(mn); mx = warp_max(mx); m2 = warp_max(m2); m3 = warp_max(m3);
+    if ((threadIdx.x & 31) == 0) {
+        int w = threadIdx.x >> 5;
+        sh[0][w] = mn; sh[1][w] = mx; sh[2][w] = m2; sh[3][w] = m3;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); k++) {
+            mn = fmin(mn, sh[0][k]); mx = fmax(mx, sh[1][k]);
+            m2 = fmax(m2, sh[2][k]); m3 = fmax(m3, sh[3][k]);
+        }
+        out[0] = mn; out[1] = mx; out[2] = m2; out[3] = m3;
+    }
+}
+
+// ---- cell-level operators for the C-ABI known-answer tests ------------------------------
+__global__ void cellop_kernel(int op, const double *__restrict__ in, double *__restrict__ out) {
+    // in: u[9], v[9], scalars[5]
+    const double *ub = in, *vb = in + 9, *sc = in + 18;
+    Stencil9 su = stencil_from_block(ub), sv = stencil_from_block(vb);
+    double r = 0.0;
+    switch (op) {
+    case 0: r = du2dx(su.w, su.c, su.e, sc[0], sc[1]); break;                     // delx, gamma
+    case 1: r = duvdx(su.c, su.s, su.w, su.sw, sv.c, sv.e, sv.w, sc[0], sc[1]); break;
+    case 2: r = duvdy(su.c, su.n, su.s, sv.c, sv.n, sv.e, sv.ne, sc[0], sc[1]); break;  // dely
+    case 3: r = dv2dy(sv.n, sv.c, sv.s, sc[0], sc[1]); break;
+    case 4: r = laplacian(su.c, su.n, su.s, su.w, su.e, sc[0], sc[1]); break;     // delx, dely
+    case 5: r = residual(su.c, su.n, su.s, su.w, su.e, sc[0], sc[1], sc[2]); break;
+    case 6: r = calculate_f(su, sv, sc[0], sc[1], sc[2], sc[3], sc[4]); break;
+    case 7: r = calculate_g(su, sv, sc[0], sc[1], sc[2], sc[3], sc[4]); break;
+    }
+    out[0] = r;
+}
+
+// rows on grid.x (2^31 limit), column blocks on grid.y
+dim3 row_grid(const Geom &g, int64_t rows, int64_t cols) {
+    (void)g;
+    return dim3((unsigned)rows, (unsigned)((cols + TPB - 1) / TPB), 1);
+}
+
+sb_status ensure_partial(sb_sim *s, size_t need) {
+    if (need <= s->partial_cap) return SB_OK;
+    if (s->d_partial) cudaFree(s->d_partial);
+    s->d_partial = nullptr;
+    SB_CUDA(cudaMalloc(&s->d_partial, need * sizeof(double)));
+    s->partial_cap = need;
+    return SB_OK;
+}
+
+}  // namespace
+
+// device array of the two pressure buffer pointers lives right after the ctl block
+static double *const *pbuf_ptr(sb_sim *s) {
+    return reinterpret_cast<double *const *>(reinterpret_cast<char *>(s->d_ctl) + 256);
+}
+
+sb_status launch_velocity_bc(sb_sim *s) {
+    if (s->bl.n == 0) return SB_OK;
+    // slab mode: redundant rows around the owned range so F/G see finished neighbours
+    int64_t row0 = s->halo ? s->g.own0 - 2 : 0, row1 = s->halo ? s->g.own1 + 2 : s->g.nxl;
+    int nb = (int)((s->bl.n + TPB - 1) / TPB);
+    velocity_bc_gather<<<nb, TPB, 0, s->stream>>>(s->g, s->u, s->v, s->cflag, s->bl, row0, row1);
+    velocity_bc_scatter<<<nb, TPB, 0, s->stream>>>(s->g, s->u, s->v, s->bl, row0, row1);
+    s->launches += 2;
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+sb_status launch_fg(sb_sim *s) {
+    int64_t row0 = s->halo ? s->g.own0 - 1 : 0, row1 = s->g.own1;
+    fg_kernel<<<row_grid(s->g, row1 - row0, s->g.NY), TPB, 0, s->stream>>>(
+        s->g, s->u, s->v, s->cflag, s->f, s->gq, row0, row1, s->prm.delx, s->prm.dely,
+        s->prm.delt, s->prm.gamma, s->prm.reynolds);
+    s->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+sb_status launch_rhs(sb_sim *s) {
+    int64_t row0 = s->g.own0, row1 = s->g.own1;
+    rhs_kernel<<<row_grid(s->g, row1 - row0, s->g.NY), TPB, 0, s->stream>>>(
+        s->g, s->f, s->gq, s->rhs, row0, row1, s->prm.delx, s->prm.dely, s->prm.delt);
+    s->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+sb_status launch_pressure_bc(sb_sim *s, int guarded) {
+    if (s->bl.n == 0) return SB_OK;
+    int nb = (int)((s->bl.n + TPB - 1) / TPB);
+    pressure_bc_kernel<<<nb, TPB, 0, s->stream>>>(s->g, pbuf_ptr(s), s->d_ctl, guarded, s->bl);
+    s->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+sb_status launch_norm_partials(sb_sim *s, int guarded, int *nblocks) {
+    int64_t rows = s->g.own1 - s->g.own0;
+    unsigned gy = (unsigned)((rows + NORM_ROWS_PER_BLOCK - 1) / NORM_ROWS_PER_BLOCK);
+    unsigned gx = (unsigned)((s->g.NY + 4 * TPB - 1) / (4 * TPB));
+    if (gx < 1) gx = 1;
+    sb_status st = ensure_partial(s, (size_t)gx * gy * 4 + 64);
+    if (st) return st;
+    norm_partial_kernel<<<dim3(gy, gx), TPB, 0, s->stream>>>(
+        s->g, pbuf_ptr(s), s->d_ctl, guarded, s->rhs, s->d_partial, s->prm.delx, s->prm.dely);
+    s->launches++;
+    SB_CUDA(cudaGetLastError());
+    *nblocks = (int)(gx * gy);
+    return SB_OK;
+}
+
+sb_status launch_sor_finalize(sb_sim *s, int nparts, double initial_norm, double eps2,
+                              int test_exit, double *norm_hist) {
+    sor_finalize_kernel<<<1, 1024, 0, s->stream>>>(s->d_ctl, s->d_partial, nparts,
+                                                   s->fluid_cells, initial_norm, eps2,
+                                                   test_exit, norm_hist);
+    s->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+sb_status reduce_norm(sb_sim *s, int nparts, double *out) {
+    sum_partials_kernel<<<1, 1024, 0, s->stream>>>(s->d_partial, nparts, s->fluid_cells,
+                                                   s->d_scalars);
+    s->launches++;
+    SB_CUDA(cudaMemcpyAsync(s->h_scalars, s->d_scalars, sizeof(double), cudaMemcpyDeviceToHost,
+                            s->stream));
+    SB_CUDA(cudaStreamSynchronize(s->stream));
+    *out = s->h_scalars[0];
+    return SB_OK;
+}
+
+static sb_status finish_ranges(sb_sim *s, int64_t nblk, double out[4]) {
+    range_final_kernel<<<1, 1024, 0, s->stream>>>(s->d_partial, nblk, s->d_scalars);
+    s->launches++;
+    SB_CUDA(cudaMemcpyAsync(s->h_scalars, s->d_scalars, 4 * sizeof(double),
+                            cudaMemcpyDeviceToHost, s->stream));
+    SB_CUDA(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < 4; i++) out[i] = s->h_scalars[i];
+    return SB_OK;
+}
+
+sb_status launch_adapt_uv(sb_sim *s) {
+    int64_t rows = s->g.own1 - s->g.own0;
+    unsigned gx = (unsigned)((s->g.NY + 4 * TPB - 1) / (4 * TPB));
+    if (gx < 1) gx = 1;
+    sb_status st = ensure_partial(s, (size_t)gx * rows * 4 + 64);
+    if (st) return st;
+    adapt_uv_kernel<<<dim3((unsigned)rows, gx), TPB, 0, s->stream>>>(
+        s->g, s->p[s->cur], s->f, s->gq, s->cflag, s->u, s->v, s->d_partial, s->prm.delt,
+        s->prm.delx, s->prm.dely);
+    s->launches++;
+    if (s->bl.n) {
+        int nb = (int)((s->bl.n + TPB - 1) / TPB);
+        restore_uv_kernel<<<nb, TPB, 0, s->stream>>>(s->g, s->u, s->v, s->bl);
+        s->launches++;
+    }
+    SB_CUDA(cudaGetLastError());
+    double out[4];
+    st = finish_ranges(s, (int64_t)gx * rows, out);
+    if (st) return st;
+    // sqrt of the folded min / max (src/grid/mod.rs:267)
+    s->speed_range[0] = sqrt(out[0]);
+    s->speed_range[1] = sqrt(out[1]);
+    s->umax = out[2];
+    s->vmax = out[3];
+    return SB_OK;
+}
+
+static sb_status launch_range(sb_sim *s, int mode, double out[4]) {
+    int64_t rows = s->g.own1 - s->g.own0;
+    unsigned gx = (unsigned)((s->g.NY + 4 * TPB - 1) / (4 * TPB));
+    if (gx < 1) gx = 1;
+    sb_status st = ensure_partial(s, (size_t)gx * rows * 4 + 64);
+    if (st) return st;
+    range_kernel<<<dim3((unsigned)rows, gx), TPB, 0, s->stream>>>(
+        s->g, mode == 0 ? s->p[s->cur] : s->u, s->v, s->cflag, s->d_partial, mode);
+    s->launches++;
+    SB_CUDA(cudaGetLastError());
+    return finish_ranges(s, (int64_t)gx * rows, out);
+}
+
+sb_status launch_pressure_range(sb_sim *s) {
+    double out[4];
+    sb_status st = launch_range(s, 0, out);
+    if (st) return st;
+    s->pressure_range[0] = out[0];
+    s->pressure_range[1] = out[1];
+    return SB_OK;
+}
+
+sb_status launch_speed_range(sb_sim *s) {
+    double out[4];
+    sb_status st = launch_range(s, 1, out);
+    if (st) return st;
+    s->speed_range[0] = sqrt(out[0]);
+    s->speed_range[1] = sqrt(out[1]);
+    s->umax = out[2];
+    s->vmax = out[3];
+    return SB_OK;
+}
+
+sb_status launch_cellop(int op, const double *u9, const double *v9, const double *scal,
+                        double *out) {
+    double h_in[23] = {0};
+    for (int i = 0; i < 9; i++) {
+        h_in[i] = u9 ? u9[i] : 0.0;
+        h_in[9 + i] = v9 ? v9[i] : 0.0;
+    }
+    for (int i = 0; i < 5; i++) h_in[18 + i] = scal[i];
+    double *d = nullptr;
+    SB_CUDA(cudaMalloc(&d, 24 * sizeof(double)));
+    SB_CUDA(cudaMemcpy(d, h_in, 23 * sizeof(double), cudaMemcpyHostToDevice));
+    cellop_kernel<<<1, 1>>>(op, d, d + 23);
+    cudaError_t e = cudaMemcpy(out, d + 23, sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        set_error(std::string("cellop: ") + cudaGetErrorString(e));
+        return SB_CUDA_ERROR;
+    }
+    return SB_OK;
+}
+
+}  // namespace sb

@@ -1,0 +1,425 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's goldens.
+
+Bar (BASELINE.json north_star):
+  * integer work (classification, boundary list): bit-exact;
+  * reference-order mode: every field bit-exact per stage and per tick; the residual
+    norm within 1e-12 relative (its summation order is the only freedom);
+  * performance mode (red-black): bit-exact against the oracle's red-black restatement,
+    and within the SOR-eps tolerance of the reference-order solution on converged ticks.
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from stroemung_b200 import math as sbmath
+from stroemung_b200 import presets, refjson
+from stroemung_b200.simulation import (SOR_RED_BLACK, SOR_REFERENCE_ORDER, BoundaryTooThinError,
+                                       Simulation)
+from tests.util import (DEFAULTS, assert_bits_equal, oracle_from, random_fields, random_mask,
+                        unfinalized)
+
+pytestmark = pytest.mark.gpu
+
+TICK = "stroemung__simulation__tests__simulation_tick"
+NORM_RTOL = 1e-12
+
+
+def close(a, b, rtol=NORM_RTOL):
+    return a == b or abs(a - b) <= rtol * max(abs(a), abs(b))
+
+
+# ---- known-answer tests on the device: src/math.rs:192-402, src/simulation.rs:449-569 ----
+def test_kat_operators_on_device(kat):
+    for c in kat["du2dx"]:
+        assert sbmath.du2dx(c["u"], c["delx"], c["gamma"]) == c["expected"]
+    for c in kat["dv2dy"]:
+        assert sbmath.dv2dy(c["v"], c["dely"], c["gamma"]) == c["expected"]
+    for c in kat["duvdx"]:
+        assert sbmath.duvdx(c["u"], c["v"], c["delx"], c["gamma"]) == c["expected"]
+    for c in kat["duvdy"]:
+        assert sbmath.duvdy(c["u"], c["v"], c["dely"], c["gamma"]) == c["expected"]
+    for c in kat["laplacian"]:
+        assert sbmath.laplacian(c["e"], c["delx"], c["dely"]) == c["expected"]
+    for name in ("calculate_f", "calculate_g"):
+        for c in kat[name]:
+            got = getattr(sbmath, name)(c["u"], c["v"], c["delx"], c["dely"], c["delt"],
+                                        c["gamma"], c["reynolds"])
+            assert got == c["expected"], (name, got, c["expected"])
+
+
+def test_residual_operator_matches_oracle():
+    rng = np.random.default_rng(7)
+    for _ in range(20):
+        blk = rng.uniform(-3, 3, 9)
+        rhs = float(rng.uniform(-5, 5))
+        assert sbmath.residual(blk, 0.1, 0.2, rhs) == po.residual(blk, 0.1, 0.2, rhs)
+
+
+# ---- the reference's simulation_tick test, on the GPU (src/simulation.rs:571-618) --------
+def check_sim_snapshot(sim, snap):
+    assert_bits_equal(sim.grid.pressure, refjson.array_from_json(snap["grid"]["pressure"]), "p")
+    assert_bits_equal(sim.grid.u, refjson.array_from_json(snap["grid"]["u"]), "u")
+    assert_bits_equal(sim.grid.v, refjson.array_from_json(snap["grid"]["v"]), "v")
+    assert sim.time == snap["time"]
+    assert sim.iterations == snap["iterations"]
+    assert sim.initial_norm_squared == snap["initial_norm_squared"]
+    assert np.array_equal(sim.grid.cell_type,
+                          refjson.cells_from_json(snap["grid"]["cell_type"])[0])
+
+
+def test_simulation_tick_golden(kat, snapshots):
+    size = (4, 3)
+    unf = unfinalized(4, 3, **{k: presets.simple_inflow(size)[k] for k in ("kind", "bu", "bv")})
+    sim = Simulation.try_from(unf)
+    it, nrm = sim.run_simulation_tick()
+    for suffix, field in (("", sim.f), ("-2", sim.g), ("-3", sim.rhs)):
+        assert_bits_equal(field, refjson.array_from_json(snapshots[TICK + suffix]["json"]),
+                          "tick1" + suffix)
+    check_sim_snapshot(sim, snapshots[TICK + "-4"]["json"])
+    a = kat["simulation_tick_asserts"]
+    assert it == a[0]["sor_iterations"] and close(nrm, a[0]["norm_squared"])
+    for _ in range(100):
+        it, nrm = sim.run_simulation_tick()
+    assert it == a[1]["sor_iterations"] and close(nrm, a[1]["norm_squared"])
+    for suffix, field in (("-5", sim.f), ("-6", sim.g), ("-7", sim.rhs)):
+        assert_bits_equal(field, refjson.array_from_json(snapshots[TICK + suffix]["json"]),
+                          "tick101" + suffix)
+    check_sim_snapshot(sim, snapshots[TICK + "-8"]["json"])
+    sim.run_ticks(100)
+    check_sim_snapshot(sim, snapshots[TICK + "-9"]["json"])
+
+
+def test_deserialize_golden(fixtures, snapshots):
+    raw = fixtures["src/test_data/small_simulation_with_boundaries.json"]["raw"]
+    prm, grid = refjson.simulation_from_json(refjson.loads(raw, quirk_serde_json=True))
+    prm["grid"] = grid
+    sim = Simulation.try_from(prm)
+    snap = snapshots["stroemung__simulation__tests__deserialize-2"]["json"]
+    assert close(sim.initial_norm_squared, snap["initial_norm_squared"])
+    assert close(sim.initial_norm_squared, 899.9547140394143)
+    # NaSt2D-derived state: one tick must match the oracle bit for bit as well
+    o = oracle_from(prm)
+    assert sim.run_simulation_tick()[0] == o.run_simulation_tick()[0]
+    assert_bits_equal(sim.grid.pressure, o.p, "p")
+    assert_bits_equal(sim.grid.u, o.u, "u")
+    # 5x7 all-fluid grid of the other fixture
+    prm, grid = refjson.simulation_from_json(
+        fixtures["src/test_data/simple_simulation.json"]["json"])
+    prm["grid"] = grid
+    sim = Simulation.try_from(prm)
+    assert sim.initial_norm_squared == 0.0
+    assert sim.grid.boundaries.fluid_cells == 35.0
+
+
+# ---- boundary classification (integer, bit-exact): src/grid/mod.rs:683-823 --------------
+def grid3(cells):
+    kind = np.zeros((3, 3), dtype=np.uint8)
+    for c in cells:
+        kind[c] = 1
+    return kind
+
+
+def test_thin_boundary():
+    for cells, first in (([(1, 0), (1, 1), (1, 2)], (1, 0)), ([(0, 1), (1, 1), (2, 1)], (0, 1))):
+        kind = grid3(cells)
+        with pytest.raises(BoundaryTooThinError) as ei:
+            Simulation.try_from(unfinalized(3, 3, kind, None, None))
+        with pytest.raises(po.BoundaryTooThin) as eo:
+            po.OracleSim(3, 3, kind=kind, **DEFAULTS)
+        assert ei.value.xy == tuple(int(x) for x in eo.value.xy) == first
+        assert ei.value.kind == 1
+
+
+def test_rebuild_boundary_list():
+    examples = [
+        ([(0, 0), (0, 1), (0, 2), (1, 0), (1, 2), (2, 0), (2, 1), (2, 2)],
+         [None, "East", None, "South", "North", None, "West", None]),
+        ([(0, 0), (0, 2), (2, 0), (2, 2)], ["SouthEast", "NorthEast", "SouthWest", "NorthWest"]),
+    ]
+    for cells, edges in examples:
+        sim = Simulation.try_from(unfinalized(3, 3, grid3(cells), None, None))
+        assert sim.grid.boundaries.sorted_boundary_list == list(zip(cells, edges))
+        assert sim.grid.boundaries.fluid_cells == 9 - len(cells)
+
+
+@pytest.mark.parametrize("shape,seed", [((34, 18), 1), ((64, 48), 2), ((257, 129), 3)])
+def test_classification_random_masks(shape, seed):
+    nx, ny = shape
+    kind, bu, bv = random_mask(nx, ny, seed)
+    sim = Simulation.try_from(unfinalized(nx, ny, kind, bu, bv))
+    o = po.OracleSim(nx, ny, kind=kind, bu=bu, bv=bv, **DEFAULTS)
+    idx, edge = sim.grid._boundary_arrays()
+    oidx, oedge = o.boundary_list()
+    assert np.array_equal(idx, oidx)
+    assert np.array_equal(edge, oedge)
+    assert sim.grid.boundaries.fluid_cells == o.state().fluid_cells
+    assert np.array_equal(sim.grid.cell_type, kind)
+    # every edge class occurs in the larger masks
+    if nx >= 64:
+        assert set(int(e) for e in oedge) == set(range(9))
+    # a thin wall somewhere in the middle: same first offender as the oracle
+    bad = kind.copy()
+    bad[nx // 2, 1:ny - 1] = 1
+    bad[nx // 2 + 1, 1:ny - 1] = 0
+    bad[nx // 2 - 1, 1:ny - 1] = 0
+    with pytest.raises(BoundaryTooThinError) as ei:
+        Simulation.try_from(unfinalized(nx, ny, bad, bu, bv))
+    with pytest.raises(po.BoundaryTooThin) as eo:
+        po.OracleSim(nx, ny, kind=bad, bu=bu, bv=bv, **DEFAULTS)
+    assert ei.value.xy == tuple(int(x) for x in eo.value.xy)
+
+
+# ---- stage-level parity, reference-order mode, random mixed-kind grids -------------------
+@pytest.mark.parametrize("shape,seed", [((34, 18), 11), ((100, 20), 12), ((257, 129), 13),
+                                        ((300, 70), 14)])
+def test_stages_bit_exact(shape, seed):
+    nx, ny = shape
+    kind, bu, bv = random_mask(nx, ny, seed)
+    p, u, v = random_fields(nx, ny, seed)
+    unf = unfinalized(nx, ny, kind, bu, bv, p=p, u=u, v=v)
+    sim = Simulation.try_from(unf)
+    o = oracle_from(unf)
+    # construction: F/G, RHS and initial norm of the raw state (no velocity BC first)
+    assert_bits_equal(sim.f, o.f, "f0")
+    assert_bits_equal(sim.g, o.g, "g0")
+    assert_bits_equal(sim.rhs, o.rhs, "rhs0")
+    assert close(sim.initial_norm_squared, o.state().initial_norm_squared)
+    assert sim.grid.pressure_range == list(o.state().pressure_range)
+    assert sim.grid.speed_range == list(o.state().speed_range)
+    # velocity BC (sequential in the reference, gather on the GPU)
+    sim.grid.set_boundary_u_and_v()
+    o.set_boundary_u_and_v()
+    assert_bits_equal(sim.grid.u, o.u, "u after BC")
+    assert_bits_equal(sim.grid.v, o.v, "v after BC")
+    sim.calculate_f_and_g()
+    o.calculate_f_and_g()
+    assert_bits_equal(sim.f, o.f, "f")
+    assert_bits_equal(sim.g, o.g, "g")
+    sim.calculate_rhs()
+    o.calculate_rhs()
+    assert_bits_equal(sim.rhs, o.rhs, "rhs")
+    # pressure BC + three lexicographic sweeps, norm after each
+    for k in range(3):
+        sim.grid.copy_pressure_to_boundaries()
+        o.copy_pressure_to_boundaries()
+        assert_bits_equal(sim.grid.pressure, o.p, f"p after BC {k}")
+        norms = sim.sor_sweeps(1)
+        o.sor_sweep()
+        assert_bits_equal(sim.grid.pressure, o.p, f"p after sweep {k}")
+        assert close(norms[0], o.calculate_norm_squared())
+        assert close(sim.calculate_norm_squared(), o.calculate_norm_squared())
+    # velocity update incl. the restore quirk and the speed range
+    sim.set_u_and_v()
+    o.set_u_and_v()
+    assert_bits_equal(sim.grid.u, o.u, "u after update")
+    assert_bits_equal(sim.grid.v, o.v, "v after update")
+    assert sim.grid.speed_range == list(o.state().speed_range)
+    sim.grid.calculate_pressure_range()
+    o.calculate_pressure_range()
+    assert sim.grid.pressure_range == list(o.state().pressure_range)
+
+
+@pytest.mark.parametrize("preset,shape,ticks", [("obstacle", (100, 20), 12),
+                                                ("simple_inflow", (34, 18), 120),
+                                                ("obstacle", (130, 66), 4)])
+def test_ticks_reference_order(preset, shape, ticks):
+    """Whole ticks: config 1 of BASELINE.json (default obstacle preset) and a channel that
+    reaches the converged regime (early exits after a few sweeps)."""
+    g = getattr(presets, preset)(shape)
+    unf = unfinalized(shape[0], shape[1], g["kind"], g["bu"], g["bv"])
+    sim = Simulation.try_from(unf)
+    o = oracle_from(unf)
+    for t in range(ticks):
+        it, nrm = sim.run_simulation_tick()
+        oit, onrm = o.run_simulation_tick()
+        assert it == oit, (t, it, oit)
+        assert close(nrm, onrm), (t, nrm, onrm)
+    assert_bits_equal(sim.grid.pressure, o.p, "p")
+    assert_bits_equal(sim.grid.u, o.u, "u")
+    assert_bits_equal(sim.grid.v, o.v, "v")
+    assert_bits_equal(sim.f, o.f, "f")
+    assert_bits_equal(sim.rhs, o.rhs, "rhs")
+    assert sim.time == o.state().time
+    assert sim.grid.speed_range == list(o.state().speed_range)
+    assert sim.grid.pressure_range == list(o.state().pressure_range)
+
+
+def test_ticks_random_state_reference_order():
+    nx, ny = 96, 40
+    kind, bu, bv = random_mask(nx, ny, 21)
+    p, u, v = random_fields(nx, ny, 21, scale=0.2)
+    unf = unfinalized(nx, ny, kind, bu, bv, p=p, u=u, v=v, max_iterations=17)
+    sim = Simulation.try_from(unf)
+    o = oracle_from(unf)
+    for t in range(5):
+        it, nrm = sim.run_simulation_tick()
+        oit, onrm = o.run_simulation_tick()
+        assert it == oit and close(nrm, onrm), (t, it, oit, nrm, onrm)
+        assert_bits_equal(sim.grid.pressure, o.p, f"p tick {t}")
+        assert_bits_equal(sim.grid.u, o.u, f"u tick {t}")
+        assert_bits_equal(sim.grid.v, o.v, f"v tick {t}")
+
+
+# ---- performance mode: red-black, temporally blocked -------------------------------------
+@pytest.mark.parametrize("T", [1, 2, 3, 4])
+@pytest.mark.parametrize("shape,seed", [((34, 18), 31), ((100, 20), 32), ((257, 129), 33),
+                                        ((150, 300), 34)])
+def test_red_black_sweeps_match_oracle(shape, seed, T):
+    nx, ny = shape
+    kind, bu, bv = random_mask(nx, ny, seed)
+    p, u, v = random_fields(nx, ny, seed)
+    unf = unfinalized(nx, ny, kind, bu, bv, p=p, u=u, v=v)
+    sim = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK, temporal_block=T)
+    o = oracle_from(unf, sor_mode=po.SOR_RED_BLACK)
+    assert close(sim.initial_norm_squared, o.state().initial_norm_squared)
+    n = 7  # not a multiple of T for T in 2..4: exercises the shortened last pass
+    norms = sim.sor_sweeps(n)
+    for k in range(n):
+        o.sor_sweep()
+        assert close(norms[k], o.calculate_norm_squared()), (k, norms[k])
+    assert_bits_equal(sim.grid.pressure, o.p, "p after red-black sweeps")
+    assert close(sim.calculate_norm_squared(), o.calculate_norm_squared())
+
+
+@pytest.mark.parametrize("T", [1, 2, 4])
+def test_red_black_ticks_match_oracle(T):
+    shape = (100, 20)
+    g = presets.obstacle(shape)
+    unf = unfinalized(shape[0], shape[1], g["kind"], g["bu"], g["bv"])
+    sim = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK, temporal_block=T)
+    o = oracle_from(unf, sor_mode=po.SOR_RED_BLACK)
+    for t in range(6):
+        it, nrm = sim.run_simulation_tick()
+        oit, onrm = o.run_simulation_tick()
+        assert it == oit and close(nrm, onrm), (t, it, oit, nrm, onrm)
+    assert_bits_equal(sim.grid.pressure, o.p, "p")
+    assert_bits_equal(sim.grid.u, o.u, "u")
+    assert_bits_equal(sim.grid.v, o.v, "v")
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 4])
+def test_red_black_early_exit_inside_block(T):
+    """Converged regime: the exit test fires after a few sweeps, often inside a temporal
+    block; the pass is then redone with the exact count and must agree with the oracle."""
+    shape = (34, 18)
+    g = presets.simple_inflow(shape)
+    unf = unfinalized(shape[0], shape[1], g["kind"], g["bu"], g["bv"])
+    sim = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK, temporal_block=T)
+    o = oracle_from(unf, sor_mode=po.SOR_RED_BLACK)
+    seen = set()
+    for t in range(260):
+        it, nrm = sim.run_simulation_tick()
+        oit, onrm = o.run_simulation_tick()
+        assert it == oit and close(nrm, onrm), (t, it, oit, nrm, onrm)
+        seen.add(it)
+    assert len(seen) > 2 and min(seen) < 100, seen
+    assert_bits_equal(sim.grid.pressure, o.p, "p")
+    assert_bits_equal(sim.grid.u, o.u, "u")
+
+
+def test_red_black_vs_reference_order_converged():
+    """Performance mode against the REFERENCE ordering (SURVEY.md 8a A6 protocol): compare
+    on converged ticks, pressure up to its free constant; tolerance = SOR epsilon."""
+    shape = (34, 18)
+    g = presets.simple_inflow(shape)
+    eps = 1e-3
+    unf = unfinalized(shape[0], shape[1], g["kind"], g["bu"], g["bv"],
+                      sor_absolute_epsilon=eps)
+    rb = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK, temporal_block=2)
+    lex = Simulation.try_from(unf, sor_mode=SOR_REFERENCE_ORDER)
+    for t in range(300):
+        it_rb, _ = rb.run_simulation_tick()
+        it_lex, _ = lex.run_simulation_tick()
+    assert it_rb < 100 and it_lex < 100  # both in the converged regime
+    fluid = g["kind"] == 0
+    du = np.abs(rb.grid.u - lex.grid.u)[fluid].max()
+    dv = np.abs(rb.grid.v - lex.grid.v)[fluid].max()
+    prb, plex = rb.grid.pressure, lex.grid.pressure
+    dp = (prb - prb[fluid].mean()) - (plex - plex[fluid].mean())
+    assert du <= eps and dv <= eps and np.abs(dp[fluid]).max() <= eps, (du, dv)
+
+
+# ---- extensions: adaptive dt, moving wall -----------------------------------------------
+def test_cavity_and_adaptive_dt_match_oracle():
+    shape = (40, 40)
+    g = presets.cavity(shape, lid_u=1.0)
+    unf = unfinalized(shape[0], shape[1], g["kind"], g["bu"], g["bv"], delx=1 / 38,
+                      dely=1 / 38, delt=1e-3, reynolds=1000.0, max_iterations=50)
+    for mode, omode in ((SOR_REFERENCE_ORDER, po.SOR_REFERENCE_ORDER),
+                        (SOR_RED_BLACK, po.SOR_RED_BLACK)):
+        sim = Simulation.try_from(unf, sor_mode=mode, tau=0.5)
+        o = oracle_from(unf, sor_mode=omode, tau=0.5)
+        for t in range(8):
+            it, nrm = sim.run_simulation_tick()
+            oit, onrm = o.run_simulation_tick()
+            assert it == oit and close(nrm, onrm), (t, it, oit, nrm, onrm)
+            assert sim.delt == o.state().delt
+        assert_bits_equal(sim.grid.u, o.u, "u")
+        assert_bits_equal(sim.grid.v, o.v, "v")
+        assert_bits_equal(sim.grid.pressure, o.p, "p")
+        assert sim.time == o.state().time
+
+
+# ---- device-side presets and cell edits --------------------------------------------------
+def test_device_presets_match_host():
+    cases = [("empty", (9, 7), ()), ("simple_inflow", (34, 18), ()), ("obstacle", (100, 20), ()),
+             ("channel_circle", (120, 64), (40, 30, 9.5)), ("backward_step", (96, 48), (24, 20)),
+             ("cavity", (32, 32), (1.5,))]
+    for name, size, args in cases:
+        if name == "channel_circle":
+            host = presets.channel_circle(size, int(args[0]), int(args[1]), args[2])
+        elif name == "backward_step":
+            host = presets.backward_step(size, int(args[0]), int(args[1]))
+        elif name == "cavity":
+            host = presets.cavity(size, args[0])
+        else:
+            host = getattr(presets, name)(size)
+        a = Simulation.from_preset(name, size, (0.1, 0.2), 0.005, 0.9, 100.0, 1e-3, 20, 1.7,
+                                   preset_args=args)
+        b = Simulation.try_from(unfinalized(size[0], size[1], host["kind"], host["bu"],
+                                            host["bv"], max_iterations=20))
+        assert np.array_equal(a.grid.cell_type, host["kind"]), name
+        assert np.array_equal(a.grid.edge_type, b.grid.edge_type), name
+        for _ in range(3):
+            assert a.run_simulation_tick() == b.run_simulation_tick(), name
+        assert_bits_equal(a.grid.u, b.grid.u, name)
+        assert_bits_equal(a.grid.pressure, b.grid.pressure, name)
+
+
+def test_draw_cells_and_rollback():
+    """src/lib.rs:38-78: paint 2x2 blocks; a block that makes a wall too thin is rolled back
+    and the previous boundary list stays in force."""
+    shape = (40, 20)
+    g = presets.simple_inflow(shape)
+    unf = unfinalized(shape[0], shape[1], g["kind"], g["bu"], g["bv"])
+    sim = Simulation.try_from(unf)
+    sim.run_ticks(3)
+    before = sim.grid.boundaries.sorted_boundary_list
+    assert sim.grid.draw_cells(1, 10, 8) is True       # 2x2 NoSlip block: fine
+    kind = g["kind"].copy()
+    kind[10:12, 8:10] = 1
+    assert np.array_equal(sim.grid.cell_type, kind)
+    assert np.all(sim.grid.u[10:12, 8:10] == 0.0)
+    after = sim.grid.boundaries.sorted_boundary_list
+    assert len(after) == len(before) + 4
+    # painting Fluid over half of it leaves a 1-wide wall -> rejected, rolled back
+    edges = sim.grid.edge_type
+    u_before = sim.grid.u
+    assert sim.grid.draw_cells(0, 11, 7) is False
+    assert np.array_equal(sim.grid.cell_type, kind)
+    assert np.array_equal(sim.grid.edge_type, edges)
+    assert_bits_equal(sim.grid.u, u_before, "u rolled back")
+    assert sim.grid.boundaries.sorted_boundary_list == after
+    # the oracle on the same edited mask agrees tick for tick afterwards
+    o = oracle_from(unf)
+    for _ in range(3):
+        o.run_simulation_tick()
+    o.kind[10:12, 8:10] = 1
+    o.u[10:12, 8:10] = 0.0
+    o.v[10:12, 8:10] = 0.0
+    o.p[10:12, 8:10] = 0.0
+    o.rebuild_boundary_list()
+    for _ in range(3):
+        assert sim.run_simulation_tick()[0] == o.run_simulation_tick()[0]
+    assert_bits_equal(sim.grid.u, o.u, "u after edit")
+    assert_bits_equal(sim.grid.pressure, o.p, "p after edit")
