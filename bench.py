@@ -1,0 +1,378 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline benchmark of stroemung_b200 (contract: see README / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c5|c1|c2|c3|c4] [--size NX NY] [--mode rb|lex] [--tblock T]
+
+One "step" is one full simulation tick (`Simulation::run_simulation_tick`,
+/root/reference/src/simulation.rs:324-333: velocity BC, F/G, RHS, SOR solve incl. the
+residual norm after every sweep, velocity update, ranges) on synthetic input.
+
+Default workload (N = 1): BASELINE.json config 5 -- the SOR-dominated full tick on an
+8192 x 8192 f64 channel grid (simple_inflow layout, fields at rest), eps = 0 and
+max_iterations = 100 so that every tick runs exactly 100 sweeps; for
+N GPUs the grid is (8192 N) x 8192, split into N row slabs (weak scaling).  The working
+set (7 f64 arrays + flags = 3.8 GB per GPU) is far larger than the 126 MB L2, so no L2
+flush is needed between timed steps.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` is the same
+metric through the C ABI with HOST buffers: every step uploads p, u, v from pinned host
+memory, ticks, and downloads p, u, v again.
+
+--impl reference times the reference's own CPU algorithm (the C oracle, single-threaded
+like the Rust original) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "Mcell-steps/s (full step incl. SOR)"
+UNIT = "Mcell-steps/s"
+SOR_BYTES_PER_CELL_SWEEP = 25.0   # read p, rhs, flag; write p
+TICK_FIXED_BYTES_PER_CELL = 81.0  # F/G+RHS 40 + velocity update/ranges 41
+# dram__bytes_read.sum + dram__bytes_write.sum per sor_rb_kernel launch, from the committed
+# `ncu --set full` capture (profiles/); None until a capture for this configuration exists
+NCU_TRAFFIC_BYTES = {}
+
+
+def workload(name, n_gpus, size=None):
+    """-> dict(preset, preset_args, size, scalar parameters) of one BASELINE config."""
+    if name == "c5":   # SOR-dominated scaling sweep: channel, 100 fixed sweeps per tick
+        nx, ny = size or (8192 * n_gpus, 8192)
+        return dict(name="c5-sor-dominated-channel", preset="simple_inflow", preset_args=(),
+                    size=(nx, ny), cell_size=(10.0 / ny, 10.0 / ny), delt=2e-4, gamma=0.9,
+                    reynolds=100.0, eps=0.0, max_iterations=100, omega=1.7)
+    if name == "c1":   # default obstacle preset, CLI defaults of the reference (src/args.rs)
+        nx, ny = size or (100, 20)
+        return dict(name="c1-obstacle-default", preset="obstacle", preset_args=(),
+                    size=(nx, ny), cell_size=(0.1, 0.2), delt=0.005, gamma=0.9,
+                    reynolds=100.0, eps=1e-3, max_iterations=100, omega=1.7)
+    if name == "c2":   # lid-driven cavity (extension kind; not expressible in the reference)
+        nx, ny = size or (1024, 1024)
+        return dict(name="c2-lid-driven-cavity", preset="cavity", preset_args=(1.0,),
+                    size=(nx, ny), cell_size=(1.0 / (nx - 2), 1.0 / (ny - 2)), delt=1e-4,
+                    gamma=0.9, reynolds=1000.0, eps=1e-3, max_iterations=1000, omega=1.7)
+    if name == "c3":   # Karman vortex street past a circle
+        nx, ny = size or (8192, 2048)
+        return dict(name="c3-karman-circle", preset="channel_circle",
+                    preset_args=(nx // 8, ny // 2, ny / 16.0), size=(nx, ny),
+                    cell_size=(4.1 / (ny - 2), 4.1 / (ny - 2)), delt=2e-4, gamma=0.9,
+                    reynolds=400.0, eps=1e-3, max_iterations=100, omega=1.7)
+    if name == "c4":   # backward-facing step
+        nx, ny = size or (16384, 4096)
+        return dict(name="c4-backward-step", preset="backward_step",
+                    preset_args=(nx // 4, ny // 2), size=(nx, ny),
+                    cell_size=(7.5 / (ny - 2), 7.5 / (ny - 2)), delt=1e-4, gamma=0.9,
+                    reynolds=200.0, eps=1e-3, max_iterations=100, omega=1.7)
+    raise SystemExit(f"unknown workload {name}")
+
+
+# ---- clocks ---------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.gpu_index)],
+                stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.split(",") for r in Path(self.tmp.name).read_text().splitlines() if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), samples=len(sm),
+                       reasons=sorted(reasons))
+        return out
+
+
+def measured_peak_gbs():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- reference arm / CPU baseline ------------------------------------------------------------
+def cpu_sample(wl, ticks, sample=(2048, 2048)):
+    """Time `ticks` full ticks of the C oracle (reference-order SOR, 1 thread -- the
+    reference is single-threaded safe Rust) on a bounded sample of the workload: the same
+    preset, parameters and sweeps per tick on a smaller grid.  Returns Mcell-steps/s."""
+    from oracle import pyoracle as po
+    from stroemung_b200 import presets
+    nx, ny = min(sample[0], wl["size"][0]), min(sample[1], wl["size"][1])
+    sub = workload(wl["name"].split("-")[0], 1, (nx, ny))  # same shape rules, smaller grid
+    a = sub["preset_args"]
+    if sub["preset"] == "channel_circle":
+        g = presets.channel_circle((nx, ny), int(a[0]), int(a[1]), float(a[2]))
+    elif sub["preset"] == "backward_step":
+        g = presets.backward_step((nx, ny), int(a[0]), int(a[1]))
+    elif sub["preset"] == "cavity":
+        g = presets.cavity((nx, ny), float(a[0]))
+    else:
+        g = getattr(presets, sub["preset"])((nx, ny))
+    kind, bu, bv = g["kind"], g["bu"], g["bv"]
+    o = po.OracleSim(nx, ny, delx=wl["cell_size"][0], dely=wl["cell_size"][1], delt=wl["delt"],
+                     gamma=wl["gamma"], reynolds=wl["reynolds"],
+                     sor_absolute_epsilon=wl["eps"], max_iterations=wl["max_iterations"],
+                     omega=wl["omega"], kind=kind, bu=bu, bv=bv)
+    t0 = time.perf_counter()
+    sweeps = 0
+    for _ in range(ticks):
+        it, _ = o.run_simulation_tick()
+        sweeps += it
+    dt = time.perf_counter() - t0
+    return {"value": nx * ny * ticks / dt / 1e6, "seconds": dt, "grid": [nx, ny],
+            "ticks": ticks, "sweeps": sweeps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = workload(args.workload, args.gpus, args.size)
+    sample = (2048, 2048) if wl["size"][0] * wl["size"][1] > 2048 * 2048 else wl["size"]
+    cpu_sample(wl, max(args.warmup, 0) and 1, sample=(256, 256))  # warm the code / caches
+    r = cpu_sample(wl, args.steps, sample)
+    sample_txt = (f"{r['grid'][0]}x{r['grid'][1]} grid of the same preset and parameters, "
+                  f"{r['ticks']} ticks, {r['sweeps']} lexicographic SOR sweeps, C oracle "
+                  f"(port of the Rust reference), 1 thread")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "grid": list(wl["size"]), "sample": sample_txt,
+                   "sweeps_per_tick": r["sweeps"] / max(r["ticks"], 1)},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": sample_txt},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---- our arm -----------------------------------------------------------------------------
+def run_ours(args):
+    from stroemung_b200 import _capi
+    from stroemung_b200.simulation import SOR_RED_BLACK, SOR_REFERENCE_ORDER, Simulation
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+    wl = workload(args.workload, n_gpus, args.size)
+    nx, ny = wl["size"]
+    mode = SOR_RED_BLACK if args.mode == "rb" else SOR_REFERENCE_ORDER
+    ext = dict(sor_mode=mode, temporal_block=args.tblock, device=local_rank)
+    if world > 1:
+        from stroemung_b200 import multi
+        multi.init_comm(dist, rank, world, local_rank)
+        xb, xe = multi.slab_range(nx, rank, world)
+        ext.update(x_begin=xb, x_end=xe, rank=rank, world=world)
+    sim = Simulation.from_preset(wl["preset"], wl["size"], wl["cell_size"], wl["delt"],
+                                 wl["gamma"], wl["reynolds"], wl["eps"], wl["max_iterations"],
+                                 wl["omega"], preset_args=wl["preset_args"], **ext)
+    L = _capi.lib()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # -- warm-up --------------------------------------------------------------------------
+    sweeps = []
+    for _ in range(args.warmup):
+        it, _ = sim.run_simulation_tick()
+    # -- timed region: device-resident ticks -----------------------------------------------
+    sampler = ClockSampler(local_rank)
+    launches0 = sim.kernel_launches
+    sim.profile_enable(True)
+    barrier()
+    sampler.start()
+    sim.timer_begin()                         # CUDA event on the stream the kernels run on
+    sor_ms = 0.0
+    for _ in range(args.steps):
+        it, nrm = sim.run_simulation_tick()   # synchronises the handle's stream at its end
+        sweeps.append(it)
+        sor_ms += sim.last_sor_ms
+    dt = sim.timer_end() * 1e-3               # event + synchronize
+    barrier()
+    clocks = sampler.stop()
+    pass_ms = sim.profile_read()
+    sim.profile_enable(False)
+    launches = sim.kernel_launches - launches0
+    dt, sor_ms = max_over_ranks(dt), max_over_ranks(sor_ms)
+    if dist is not None:
+        import torch
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+    cells = nx * ny
+    value = cells * args.steps / dt / 1e6
+    total_sweeps = sum(sweeps)
+
+    # -- end-to-end: host buffers in, host buffers out, every step --------------------------
+    rows = sim._local_shape[0]
+    nbytes = rows * ny * 8
+    host = [C.c_void_p(L.sb_host_alloc(nbytes)) for _ in range(3)]
+    fields = (_capi.FIELD_P, _capi.FIELD_U, _capi.FIELD_V)
+    for hbuf, fld in zip(host, fields):
+        sim._check(L.sb_download(sim._h, fld, hbuf))
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    sim.timer_begin()
+    for _ in range(e2e_steps):
+        for hbuf, fld in zip(host, fields):
+            sim._check(L.sb_upload(sim._h, fld, hbuf))      # H2D from pinned host memory
+        sim.run_simulation_tick()
+        for hbuf, fld in zip(host, fields):
+            sim._check(L.sb_download(sim._h, fld, hbuf))    # D2H of the step's result
+    dt_e2e = max_over_ranks(sim.timer_end() * 1e-3)
+    barrier()
+    for hbuf in host:
+        L.sb_host_free(hbuf)
+    e2e_value = cells * e2e_steps / dt_e2e / 1e6
+
+    # -- roofline of the dominant kernel (the SOR pass) -------------------------------------
+    peak, peak_src = measured_peak_gbs()
+    T = sim.temporal_block if args.mode == "rb" else 1
+    work = [m for m in pass_ms if m > 0.2 * (max(pass_ms) if len(pass_ms) else 1.0)]
+    local_cells = rows * ny
+    roof = None
+    if work:
+        avg_ms = sum(work) / len(work)
+        sweeps_per_launch = total_sweeps / len(work)
+        alg_bytes = SOR_BYTES_PER_CELL_SWEEP * local_cells * sweeps_per_launch
+        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+        key = f"{args.mode}-T{T}-{rows}x{ny}"
+        roof = {"bound": "hbm", "kernel": "sor_rb_kernel" if args.mode == "rb" else "sor_lex_kernel",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": NCU_TRAFFIC_BYTES.get(key),
+                "peak_source": peak_src, "launches_timed": len(work),
+                "avg_launch_ms": avg_ms, "sweeps_per_launch": sweeps_per_launch,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "25 B per cell-sweep x cells x sweeps per launch; CUDA events around "
+                        "every launch of the timed region"}
+    if rank != 0:
+        return 0
+
+    # -- CPU baseline beside it (N = 1 only): bounded sample of the same workload -----------
+    cpu = None
+    if n_gpus == 1 and not args.no_cpu:
+        sample = (2048, 2048) if cells > 2048 * 2048 else wl["size"]
+        r = cpu_sample(wl, 2 if cells > 2048 * 2048 else min(args.steps, 20), sample)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{r['grid'][0]}x{r['grid'][1]} grid of the same preset/parameters, "
+                         f"{r['ticks']} ticks, {r['sweeps']} lexicographic sweeps, "
+                         f"{r['seconds']:.1f} s, C oracle (port of the Rust reference), 1 thread"}
+
+    kfix = TICK_FIXED_BYTES_PER_CELL
+    k_avg = total_sweeps / max(args.steps, 1)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "grid": [nx, ny], "sor_mode": args.mode,
+                   "temporal_block": T, "sweeps_per_tick": k_avg,
+                   "slabs": f"{n_gpus} row slab(s) along x",
+                   "l2": "working set 3.8 GB per GPU >> 126 MB L2, no flush needed"},
+        "sor": {"gcell_sweeps_per_s": cells * total_sweeps / (sor_ms * 1e-3) / 1e9
+                if sor_ms else None,
+                "algorithmic_gbs": SOR_BYTES_PER_CELL_SWEEP * cells * total_sweeps /
+                (sor_ms * 1e-3) / 1e9 if sor_ms else None,
+                "ms_per_tick": sor_ms / max(args.steps, 1)},
+        "tick_roofline": {"bytes_per_cell": kfix + SOR_BYTES_PER_CELL_SWEEP * k_avg,
+                          "roofline_mcell_steps_per_s": n_gpus * peak * 1e9 /
+                          (kfix + SOR_BYTES_PER_CELL_SWEEP * k_avg) / 1e6,
+                          "frac": value / (n_gpus * peak * 1e9 /
+                                           (kfix + SOR_BYTES_PER_CELL_SWEEP * k_avg) / 1e6)},
+        "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * nbytes * n_gpus,
+                "d2h_bytes_per_step": 3 * nbytes * n_gpus, "steps": e2e_steps},
+        "gpu_launches": launches,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5")
+    ap.add_argument("--size", type=int, nargs=2, default=None)
+    ap.add_argument("--mode", default="rb", choices=["rb", "lex"])
+    ap.add_argument("--tblock", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.size is not None:
+        args.size = tuple(args.size)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

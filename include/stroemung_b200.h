@@ -222,6 +222,15 @@ uint64_t sb_kernel_launches(const sb_sim *sim);
 /* device time (ms) of the SOR solve inside the last sb_tick / sb_solve_sor / sb_sor_sweeps,
  * measured with CUDA events on the handle's stream */
 double sb_last_sor_ms(const sb_sim *sim);
+/* per-pass profiling of the dominant kernel: when enabled, every SOR sweep-kernel launch
+ * (red-black pass or wavefront sweep) is bracketed by CUDA events on the handle's stream.
+ * sb_profile_read returns the durations (ms) recorded since the last read, oldest first;
+ * launches that found the solve already finished (no-op passes) are included. */
+sb_status sb_profile_enable(sb_sim *sim, int32_t enable);
+sb_status sb_profile_read(sb_sim *sim, double *ms, size_t capacity, size_t *n);
+/* device-side stopwatch: CUDA events recorded on the handle's stream */
+sb_status sb_timer_begin(sb_sim *sim);
+sb_status sb_timer_end(sb_sim *sim, double *elapsed_ms); /* synchronises the stream */
 /* raw CUDA stream of the handle (cudaStream_t) so a host can bracket it with events */
 void *sb_stream(const sb_sim *sim);
 const char *sb_version(void);

@@ -64,7 +64,8 @@ SYMBOLS = [
     "sb_edit_cells", "sb_create_preset", "sb_error_cell", "sb_last_error_string",
     "sb_comm_unique_id", "sb_comm_init", "sb_comm_finalize", "sb_du2dx", "sb_duvdx", "sb_duvdy",
     "sb_dv2dy", "sb_laplacian", "sb_residual", "sb_calculate_f", "sb_calculate_g",
-    "sb_kernel_launches", "sb_last_sor_ms", "sb_stream", "sb_version",
+    "sb_profile_enable", "sb_profile_read", "sb_timer_begin", "sb_timer_end", "sb_kernel_launches", "sb_last_sor_ms", "sb_stream",
+    "sb_version",
 ]
 
 _lib = None
@@ -117,6 +118,10 @@ def lib():
         "sb_residual": ([dp, d, d, d, dp], C.c_int),
         "sb_calculate_f": ([dp, dp, d, d, d, d, d, dp], C.c_int),
         "sb_calculate_g": ([dp, dp, d, d, d, d, d, dp], C.c_int),
+        "sb_profile_enable": ([vp, C.c_int32], C.c_int),
+        "sb_profile_read": ([vp, dp, C.c_size_t, C.POINTER(C.c_size_t)], C.c_int),
+        "sb_timer_begin": ([vp], C.c_int),
+        "sb_timer_end": ([vp, dp], C.c_int),
         "sb_kernel_launches": ([vp], C.c_uint64),
         "sb_last_sor_ms": ([vp], C.c_double),
         "sb_stream": ([vp], vp),

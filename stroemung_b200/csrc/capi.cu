@@ -22,6 +22,17 @@ static thread_local uint8_t g_err_kind = 0;
 
 void set_error(const std::string &msg) { g_error = msg; }
 
+void prof_mark(sb_sim *s) {
+    if (!s->profiling) return;
+    if (s->prof_used == s->prof_events.size()) {
+        if (s->prof_events.size() >= 8192) return;  // bounded
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        s->prof_events.push_back(e);
+    }
+    cudaEventRecord(s->prof_events[s->prof_used++], s->stream);
+}
+
 static bool is_rb(const sb_sim *s) { return s->prm.sor_mode == SB_SOR_RED_BLACK; }
 
 static sb_status validate(const sb_params *p) {
@@ -57,8 +68,11 @@ static void destroy(sb_sim *s) {
     cudaFree(s->d_scan); cudaFree(s->d_err);
     if (s->h_scalars) cudaFreeHost(s->h_scalars);
     if (s->h_ctl) cudaFreeHost(s->h_ctl);
+    for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     if (s->ev_sor0) cudaEventDestroy(s->ev_sor0);
     if (s->ev_sor1) cudaEventDestroy(s->ev_sor1);
+    if (s->ev_t0) cudaEventDestroy(s->ev_t0);
+    if (s->ev_t1) cudaEventDestroy(s->ev_t1);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -133,6 +147,8 @@ static sb_status allocate(const sb_params *params, sb_sim **out) {
                            cudaMemcpyHostToDevice, s->stream));
     SB_TRY(cudaEventCreate(&s->ev_sor0));
     SB_TRY(cudaEventCreate(&s->ev_sor1));
+    SB_TRY(cudaEventCreate(&s->ev_t0));
+    SB_TRY(cudaEventCreate(&s->ev_t1));
     SB_TRY(cudaStreamSynchronize(s->stream));
 #undef SB_TRY
     s->time = params->time;
@@ -770,6 +786,45 @@ sb_status sb_calculate_f(const double u[9], const double v[9], double delx, doub
 sb_status sb_calculate_g(const double u[9], const double v[9], double delx, double dely,
                          double delt, double gamma, double reynolds, double *out) {
     return cellop(7, u, v, delx, dely, delt, gamma, reynolds, out);
+}
+
+sb_status sb_profile_enable(sb_sim *sim, int32_t enable) {
+    SB_ENTER(sim);
+    SB_CUDA(cudaStreamSynchronize(sim->stream));
+    sim->profiling = enable != 0;
+    sim->prof_used = 0;
+    return SB_OK;
+}
+
+sb_status sb_profile_read(sb_sim *sim, double *ms, size_t capacity, size_t *n) {
+    SB_ENTER(sim);
+    SB_CUDA(cudaStreamSynchronize(sim->stream));
+    size_t pairs = sim->prof_used / 2;
+    if (n) *n = pairs;
+    for (size_t i = 0; i < pairs && i < capacity && ms; i++) {
+        float t = 0.f;
+        SB_CUDA(cudaEventElapsedTime(&t, sim->prof_events[2 * i], sim->prof_events[2 * i + 1]));
+        ms[i] = t;
+    }
+    sim->prof_used = 0;
+    return SB_OK;
+}
+
+sb_status sb_timer_begin(sb_sim *sim) {
+    SB_ENTER(sim);
+    SB_CUDA(cudaStreamSynchronize(sim->stream));
+    SB_CUDA(cudaEventRecord(sim->ev_t0, sim->stream));
+    return SB_OK;
+}
+
+sb_status sb_timer_end(sb_sim *sim, double *elapsed_ms) {
+    SB_ENTER(sim);
+    SB_CUDA(cudaEventRecord(sim->ev_t1, sim->stream));
+    SB_CUDA(cudaEventSynchronize(sim->ev_t1));
+    float ms = 0.f;
+    SB_CUDA(cudaEventElapsedTime(&ms, sim->ev_t0, sim->ev_t1));
+    if (elapsed_ms) *elapsed_ms = ms;
+    return SB_OK;
 }
 
 uint64_t sb_kernel_launches(const sb_sim *sim) { return sim ? sim->launches : 0; }

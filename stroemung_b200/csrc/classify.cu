@@ -39,13 +39,22 @@ __global__ void edge_kernel(uint8_t *__restrict__ cflag, Geom g,
             int kind = cf_kind(fl);
             if (kind == SB_KIND_FLUID) {
                 if (lx >= g.own0 && lx < g.own1) fluid = 1;
+                // CF_NEAR: some 4-neighbour inside the grid is not fluid (neighbours this
+                // slab cannot see count as "not fluid": the flag only has to be conservative)
+                bool near = false;
+                if (g.gx0 + lx > 0) near |= !(lx > 0 && cf_is_fluid(cflag[c - g.pitch]));
+                if (g.gx0 + lx < g.NX - 1)
+                    near |= !(lx + 1 < g.nxl && cf_is_fluid(cflag[c + g.pitch]));
+                if (y > 0) near |= !cf_is_fluid(cflag[c - 1]);
+                if (y + 1 < g.NY) near |= !cf_is_fluid(cflag[c + 1]);
+                cflag[c] = (uint8_t)(CF_FLUID | (near ? CF_NEAR : 0));
             } else {
                 // neighbour bytes may be rewritten concurrently, but only their edge
                 // bits change; kind and valid bits are stable
-                bool w = lx > 0 && cf_is_fluid(cflag[c - g.pitch] & 0x87);
-                bool e = lx + 1 < g.nxl && cf_is_fluid(cflag[c + g.pitch] & 0x87);
-                bool n = y > 0 && cf_is_fluid(cflag[c - 1] & 0x87);
-                bool s = y + 1 < g.NY && cf_is_fluid(cflag[c + 1] & 0x87);
+                bool w = lx > 0 && cf_is_fluid(cflag[c - g.pitch]);
+                bool e = lx + 1 < g.nxl && cf_is_fluid(cflag[c + g.pitch]);
+                bool n = y > 0 && cf_is_fluid(cflag[c - 1]);
+                bool s = y + 1 < g.NY && cf_is_fluid(cflag[c + 1]);
                 int m = (w << 3) | (e << 2) | (n << 1) | (int)s;
                 uint8_t edge = c_edge_of_mask[m];
                 if (edge == 0xFF) {
@@ -164,7 +173,7 @@ __global__ void fill_kernel(const uint8_t *__restrict__ cflag, Geom g,
             int64_t cidx = lx * g.pitch + y;
             uint8_t fl = cflag[cidx];
             lin[pos] = cidx;
-            ke[pos] = (uint8_t)(cf_kind(fl) | (cf_edge(fl) << 3));
+            ke[pos] = (uint8_t)(cf_kind(fl) | (cf_edge(fl) << 3));  // listed cells are not fluid
             bu[pos] = 0.0;
             bv[pos] = 0.0;
             pos++;

@@ -21,18 +21,29 @@ __global__ void mark_valid_kernel(Geom g, uint8_t *__restrict__ cflag,
     int64_t gx = g.gx0 + lx;
     uint8_t out = 0;
     if (y < g.NY && gx >= 0 && gx < g.NX) {
-        uint8_t kind = kind_rows ? kind_rows[c] : (uint8_t)(cflag[c] & 7);
-        uint8_t edge_bits = keep_edges ? (uint8_t)(cflag[c] & 0x78) : (uint8_t)0;
-        out = (uint8_t)(CF_VALID | (kind & 7) | edge_bits);
+        uint8_t old = cflag[c];
+        uint8_t kind = kind_rows ? kind_rows[c] : (uint8_t)(old & 7);
+        uint8_t bits = 0;
+        if (keep_edges) {
+            // like the reference, BCs keep using the stale classification until the list is
+            // rebuilt; a cell that turns fluid gets the conservative CF_NEAR
+            if ((kind & 7) == SB_KIND_FLUID) bits = CF_NEAR;
+            else if (!cf_is_fluid(old)) bits = (uint8_t)(old & 0x78);
+        }
+        out = (uint8_t)(CF_VALID | (kind & 7) | bits);
     }
     cflag[c] = out;
 }
 
+// edge bits of boundary cells are cleared (the list kernel puts the old ones back); fluid
+// cells get a conservative CF_NEAR until the next successful classification
 __global__ void clear_edges_kernel(Geom g, uint8_t *__restrict__ cflag) {
     int64_t y = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     int64_t lx = blockIdx.x;
     if (y >= g.pitch || lx >= g.nxl) return;
-    cflag[lx * g.pitch + y] &= 0x87;
+    uint8_t f = cflag[lx * g.pitch + y] & 0x87;
+    if (f == CF_FLUID) f |= CF_NEAR;
+    cflag[lx * g.pitch + y] = f;
 }
 
 __global__ void list_edges_kernel(uint8_t *__restrict__ cflag, BList bl) {

@@ -14,14 +14,19 @@
 namespace sb {
 
 // ---- per-cell flag byte (device representation of Cell + Option<EdgeType>) -----
-// bits 0-2 kind (sb_kind), bits 3-6 edge (sb_edge), bit 7 = cell exists.
-// 0x00 therefore means "outside the grid" -- what TMA's out-of-bounds zero fill and
-// unowned slab rows produce -- and such cells are inert everywhere.
+// bits 0-2 kind (sb_kind), bit 7 = cell exists; bits 3-6: for a boundary cell its edge
+// class (sb_edge), for a fluid cell bit 3 = "has a non-fluid 4-neighbour" (CF_NEAR).
+// 0x00 therefore means "outside the grid" -- what out-of-bounds reads and unowned slab
+// rows produce -- and such cells are inert everywhere.
 constexpr uint8_t CF_VALID = 0x80;
 constexpr uint8_t CF_FLUID = CF_VALID | SB_KIND_FLUID;
+constexpr uint8_t CF_NEAR = 0x08;
 __host__ __device__ __forceinline__ int cf_kind(uint8_t f) { return f & 7; }
-__host__ __device__ __forceinline__ int cf_edge(uint8_t f) { return (f >> 3) & 15; }
-__host__ __device__ __forceinline__ bool cf_is_fluid(uint8_t f) { return f == CF_FLUID; }
+__host__ __device__ __forceinline__ bool cf_is_fluid(uint8_t f) { return (f & 0x87) == CF_FLUID; }
+// edge class of a boundary cell (0 for fluid cells, whose bits 3-6 mean something else)
+__host__ __device__ __forceinline__ int cf_edge(uint8_t f) {
+    return cf_is_fluid(f) ? 0 : (f >> 3) & 15;
+}
 // a boundary cell of the grid (present and not fluid)
 __host__ __device__ __forceinline__ bool cf_is_boundary(uint8_t f) {
     return (f & CF_VALID) && (f & 7) != SB_KIND_FLUID;
@@ -117,8 +122,12 @@ struct sb_sim {
     uint64_t err_xy[2] = {0, 0};
     uint8_t err_kind = 0;
     uint64_t launches = 0;
-    cudaEvent_t ev_sor0 = nullptr, ev_sor1 = nullptr;
+    cudaEvent_t ev_sor0 = nullptr, ev_sor1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     double last_sor_ms = 0.0;
+    // optional per-pass event profiling (sb_profile_enable)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;  // pairs: begin, end
+    size_t prof_used = 0;
     // tensor maps for the red-black pass (built lazily per buffer)
     bool tmaps_ready = false;
     CUtensorMap tm_p[2], tm_rhs, tm_flag;
@@ -146,6 +155,8 @@ sb_status launch_sor_lex_sweep(sb_sim *s, int guarded);
 // sor_rb.cu
 sb_status launch_sor_rb_pass(sb_sim *s, int *ntiles, int norm_only);
 int rb_halo_rows(int T);
+// profiling hooks (capi.cu): record an event of the current pass on the stream
+void prof_mark(sb_sim *s);
 // finalize (stages.cu): sum partials, exit test, update ctl
 sb_status launch_sor_finalize(sb_sim *s, int nparts, double initial_norm, double eps2,
                               int test_exit, double *norm_hist);

@@ -133,9 +133,11 @@ sb_status launch_sor_lex_sweep(sb_sim *s, int guarded) {
     double dely2 = s->prm.dely * s->prm.dely;
     double one_minus_w = 1.0 - s->prm.omega;
     double middle = s->prm.omega / ((2.0 / delx2) + (2.0 / dely2));
+    prof_mark(s);
     sor_lex_kernel<<<nbands, 32, 0, s->stream>>>(g, pbuf_ptr(s), s->d_ctl, guarded, s->rhs,
                                                  s->cflag, s->d_lex_sync, delx2, dely2,
                                                  one_minus_w, middle);
+    prof_mark(s);
     s->launches++;
     SB_CUDA(cudaGetLastError());
     return SB_OK;

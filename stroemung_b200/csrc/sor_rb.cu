@@ -6,22 +6,33 @@
 // (src/grid/mod.rs:343-412), the sweep (:253-274, here as a red half-sweep over
 // (x+y) even then a black half-sweep) and calculate_norm_squared (:216-227).
 //
-// One CTA owns a TXR x TW tile (x rows, y columns; y contiguous) staged into shared
-// memory by two TMA box loads (p, rhs; out-of-grid cells arrive as zeros).  The u8 cell
-// flags are read with plain 16-bit loads while the TMA is in flight: a TMA box must start
-// on a 16-byte boundary, which an odd-sized halo of 1-byte cells cannot honour; cells
-// outside the grid get flag 0 = "not a cell".  The tile carries a halo of h = 2T+1 cells: after sweep k
-// the values at distance >= 2k from the tile edge are exact, so T sweeps leave the
-// inner (TXR-2h) x (TW-2h-2) region exact, together with the residuals of all T
-// sweeps.  That region is written to the other pressure buffer (ping-pong), and one
-// partial sum of squared residuals per sweep and tile goes to the finalize kernel.
+// One CTA owns a TXR x TW tile (x rows, y columns; y contiguous).  p and rhs are staged
+// into shared memory by two TMA box loads (out-of-grid cells arrive as zeros); the u8 cell
+// flags are read with plain 16-bit loads while the TMA is in flight (a TMA box must start
+// on a 16-byte boundary, which a halo of 1-byte cells cannot honour) and condensed into
+// per-thread bit masks.  Each thread owns two adjacent columns of RPT rows and keeps their
+// pressures IN REGISTERS for the whole pass; shared memory only serves the exchange with
+// the neighbouring threads (one foreign column neighbour per update, two halo rows per
+// half-sweep) and the rhs reads.  Row parity is a template parameter and the row loops are
+// fully unrolled, so which cell of a pair has which colour is known at compile time.
+//
+// Halo: the tile carries h = 2T+2 cells.  Boundary cells on the outermost tile ring cannot
+// take their pressure BC (their fluid neighbour may lie outside the tile), so after sweep k
+// the fluid values at distance >= 2k+1 from the tile edge are exact; T sweeps leave the
+// inner (TXR-2h) x (TW-2h) region exact together with its residuals (which read neighbours
+// at distance h-1 = 2T+1) for all T sweeps.  That region is written to the other pressure
+// buffer (ping-pong); one partial sum of squared residuals per sweep and tile goes to the
+// finalize kernel.
+//
+// Residuals ride along: a black cell's residual is taken right after its update (all its
+// neighbours are final); a red cell's residual of sweep k is evaluated inside the red
+// half-sweep of sweep k+1, where the same stencil sum t is needed anyway and none of its
+// inputs has changed.  Only red cells next to a non-fluid cell (whose boundary pressures
+// are refreshed in between), non-fluid cells, and the last sweep of a pass need an explicit
+// residual evaluation.  The values are bit-identical either way.
 //
 // HBM traffic per launch and cell: 8 (p in) + 8 (rhs) + 1 (flag) + 8 (p out) = 25 B for
 // T sweeps (halo re-reads are served by L2), i.e. 25/T B per cell-sweep.
-//
-// Each thread owns two adjacent columns (one 16-byte shared-memory word) of a run of
-// rows and walks them with a 3-row register window, so a half-sweep reads each
-// pressure value once per thread plus one foreign column neighbour.
 //
 // Arithmetic (identical in oracle/stroemung_oracle.c, SO_SOR_RED_BLACK):
 //     t     = fma(1/dx^2, pE+pW, fma(1/dy^2, pS+pN, -rhs))
@@ -41,8 +52,10 @@ constexpr int TROWS = NTHR / TCOLS;     // thread rows
 constexpr int RPT = TXR / TROWS;        // rows per thread
 constexpr int TMAX = 4;
 constexpr int TILE = TXR * TW;
-constexpr size_t SMEM_BYTES = (size_t)TILE * 17 + 64 + (NTHR / 32) * TMAX * sizeof(double);
-static_assert(TXR % TROWS == 0, "rows must split evenly");
+constexpr int NWARP = NTHR / 32;
+constexpr size_t SMEM_BYTES = (size_t)TILE * 17 + 64 + NWARP * TMAX * sizeof(double);
+static_assert(TXR % TROWS == 0 && RPT % 2 == 0, "rows must split evenly, even per thread");
+static_assert(2 * RPT <= 32, "cell masks are 32-bit");
 
 struct RbConsts {
     double rdx2, rdy2, diag, mid, omw;
@@ -88,119 +101,110 @@ __device__ __forceinline__ double2 lds2(const double *sp, int idx) {
 }
 
 // pressure BC of one boundary cell from its fluid neighbours (src/grid/mod.rs:351-399)
-__device__ __forceinline__ void bc_cell(double *sp, int idx, int edge) {
+__device__ __forceinline__ double bc_value(const double *sp, int idx, int edge) {
     switch (edge) {
-    case SB_EDGE_N: sp[idx] = sp[idx - 1]; break;
-    case SB_EDGE_NE: sp[idx] = (sp[idx - 1] + sp[idx + TW]) / 2.0; break;
-    case SB_EDGE_E: sp[idx] = sp[idx + TW]; break;
-    case SB_EDGE_SE: sp[idx] = (sp[idx + 1] + sp[idx + TW]) / 2.0; break;
-    case SB_EDGE_S: sp[idx] = sp[idx + 1]; break;
-    case SB_EDGE_SW: sp[idx] = (sp[idx + 1] + sp[idx - TW]) / 2.0; break;
-    case SB_EDGE_W: sp[idx] = sp[idx - TW]; break;
-    case SB_EDGE_NW: sp[idx] = (sp[idx - 1] + sp[idx - TW]) / 2.0; break;
-    default: break;
+    case SB_EDGE_N: return sp[idx - 1];
+    case SB_EDGE_NE: return (sp[idx - 1] + sp[idx + TW]) / 2.0;
+    case SB_EDGE_E: return sp[idx + TW];
+    case SB_EDGE_SE: return (sp[idx + 1] + sp[idx + TW]) / 2.0;
+    case SB_EDGE_S: return sp[idx + 1];
+    case SB_EDGE_SW: return (sp[idx + 1] + sp[idx - TW]) / 2.0;
+    case SB_EDGE_W: return sp[idx - TW];
+    case SB_EDGE_NW: return (sp[idx - 1] + sp[idx - TW]) / 2.0;
+    default: return sp[idx];
     }
 }
 
-struct TileCtx {
-    int r_begin, col0;      // first tile row / first (even) tile column of this thread
-    int64_t gx_base, gy0;   // global x of tile row 0, global y of col0
-    int64_t NX, NY;
-    int64_t own_gx0, own_gx1;  // owned global rows (norm is counted there only)
-    int h, hy;
+// both cell bits of the thread's rows i with r_begin + i in [lo, hi)
+__device__ __forceinline__ uint32_t row_bits(int lo, int hi, int r_begin) {
+    const int a = min(max(lo - r_begin, 0), RPT), b = min(max(hi - r_begin, 0), RPT);
+    if (b <= a) return 0u;
+    return ((1u << (2 * b)) - 1u) & ~((1u << (2 * a)) - 1u);
+}
+
+// per-thread cell masks; bit 2*i + e is cell (row r_begin + i, column col0 + e)
+struct Masks {
+    uint32_t upd;   // fluid, interior of the grid, not on the tile ring: swept
+    uint32_t cnt;   // in the tile's exact inner region, interior, owned: counts in the norm
+    uint32_t exp_;  // counted cells whose residual needs an explicit evaluation every sweep
+    uint32_t bc;    // boundary cells with an edge class, not on the tile ring: take the BC
 };
 
-__device__ __forceinline__ bool interior(const TileCtx &c, int64_t gx, int64_t gy) {
-    return gx >= 1 && gx <= c.NX - 2 && gy >= 1 && gy <= c.NY - 2;
+// bits of the cells with colour 0 (red) when the thread's first row has parity PAR
+template <int PAR>
+__host__ __device__ constexpr uint32_t red_mask() {
+    uint32_t m = 0;
+    for (int i = 0; i < RPT; i++) m |= 1u << (2 * i + ((PAR ^ i) & 1));
+    return m;
 }
 
-// one colour of one sweep over this thread's cells; colour 1 also folds the residuals of
-// the black fluid cells it updates into acc (their neighbours are already final)
-template <int COLOUR>
-__device__ __forceinline__ void half_sweep(double *sp, const double *sr, const uint8_t *sf,
-                                           const TileCtx &c, const RbConsts &k, double &acc) {
-    int r0 = max(c.r_begin, 1), r1 = min(c.r_begin + RPT, TXR - 1);
-    double2 pm = lds2(sp, (r0 - 1) * TW + c.col0);
-    double2 pc = lds2(sp, r0 * TW + c.col0);
-#pragma unroll 4
-    for (int r = r0; r < r1; r++) {
-        double2 pn = lds2(sp, (r + 1) * TW + c.col0);
-        const int64_t gx = c.gx_base + r;
-        const int sel = (int)((gx + c.gy0 + COLOUR) & 1);  // which cell of the pair has this colour
-        const int col = c.col0 + sel;
-        const int idx = r * TW + col;
-        const bool upd = sf[idx] == CF_FLUID && col >= 1 && col <= TW - 2 &&
-                         interior(c, gx, c.gy0 + sel);
-        if (upd) {
-            const double pE = sel ? pn.y : pn.x, pW = sel ? pm.y : pm.x;
-            double pN, pS, pold;
-            if (sel == 0) { pS = pc.y; pN = sp[idx - 1]; pold = pc.x; }
-            else          { pN = pc.x; pS = sp[idx + 1]; pold = pc.y; }
-            const double t = fma(k.rdx2, pE + pW, fma(k.rdy2, pS + pN, -sr[idx]));
-            const double pnew = fma(k.mid, t, k.omw * pold);
-            sp[idx] = pnew;
-            if (sel == 0) pc.x = pnew; else pc.y = pnew;
-            if (COLOUR == 1) {
-                const bool owned = r >= c.h && r < TXR - c.h && col >= c.hy && col < TW - c.hy &&
-                                   gx >= c.own_gx0 && gx < c.own_gx1;
-                if (owned) {
-                    const double rr = fma(-k.diag, pnew, t);
-                    acc = fma(rr, rr, acc);
-                }
+// stencil sum t of cell (row i, component sel) from registers + one shared-memory neighbour
+#define SB_T_OF_CELL(i, sel)                                                            \
+    const double2 &Pm_ = (i) == 0 ? up : P[(i) == 0 ? 0 : (i)-1];                       \
+    const double2 &Pn_ = (i) == RPT - 1 ? dn : P[(i) == RPT - 1 ? RPT - 1 : (i) + 1];   \
+    const int idx_ = base + (i)*TW + (sel);                                             \
+    const double pE_ = (sel) ? Pn_.y : Pn_.x, pW_ = (sel) ? Pm_.y : Pm_.x;              \
+    const double pS_ = (sel) ? sp[idx_ + 1] : P[i].y;                                   \
+    const double pN_ = (sel) ? P[i].x : sp[idx_ - 1];                                   \
+    const double t_ = fma(k.rdx2, pE_ + pW_, fma(k.rdy2, pS_ + pN_, -sr[idx_]));
+
+// one colour of one sweep.  COLOUR 0 (red): cells in m_lag also contribute the residual of
+// the PREVIOUS sweep to acc_prev.  COLOUR 1 (black): counted cells contribute this sweep's
+// residual to acc_cur.
+template <int PAR, int COLOUR>
+__device__ __forceinline__ void half_sweep(double2 (&P)[RPT], double *sp, const double *sr,
+                                           int base, int r_begin, const Masks &m, uint32_t m_lag,
+                                           const RbConsts &k, double &acc_prev, double &acc_cur) {
+    const double2 up = r_begin > 0 ? lds2(sp, base - TW) : make_double2(0.0, 0.0);
+    const double2 dn = r_begin + RPT < TXR ? lds2(sp, base + RPT * TW) : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < RPT; i++) {
+        const int sel = (PAR ^ i ^ COLOUR) & 1;
+        const uint32_t bit = 1u << (2 * i + sel);
+        if (m.upd & bit) {
+            SB_T_OF_CELL(i, sel)
+            const double pold = sel ? P[i].y : P[i].x;
+            if (COLOUR == 0 && (m_lag & bit)) {
+                const double rr = fma(-k.diag, pold, t_);
+                acc_prev = fma(rr, rr, acc_prev);
+            }
+            const double pnew = fma(k.mid, t_, k.omw * pold);
+            if (sel) P[i].y = pnew; else P[i].x = pnew;
+            sp[idx_] = pnew;
+            if (COLOUR == 1 && (m.cnt & bit)) {
+                const double rr = fma(-k.diag, pnew, t_);
+                acc_cur = fma(rr, rr, acc_cur);
             }
         }
-        pm = pc;
-        pc = pn;
     }
 }
 
-// residuals of the owned interior cells not covered by the black half-sweep:
-// every red cell, and black cells that are not fluid (obstacle cells count in the norm,
-// src/simulation.rs:216-227 sums over ALL interior cells)
-__device__ __forceinline__ void norm_rest(const double *sp, const double *sr, const uint8_t *sf,
-                                          const TileCtx &c, const RbConsts &k, double &acc,
-                                          bool all_black) {
-    int r0 = max(c.r_begin, c.h), r1 = min(c.r_begin + RPT, TXR - c.h);
-    if (c.col0 < c.hy || c.col0 >= TW - c.hy || r0 >= r1) return;
-    double2 pm = lds2(sp, (r0 - 1) * TW + c.col0);
-    double2 pc = lds2(sp, r0 * TW + c.col0);
-#pragma unroll 4
-    for (int r = r0; r < r1; r++) {
-        double2 pn = lds2(sp, (r + 1) * TW + c.col0);
-        const int64_t gx = c.gx_base + r;
-        if (gx >= c.own_gx0 && gx < c.own_gx1) {
-            const int sel = (int)((gx + c.gy0) & 1);  // the red cell of the pair
-            {
-                const int idx = r * TW + c.col0 + sel;
-                if (interior(c, gx, c.gy0 + sel)) {
-                    const double pE = sel ? pn.y : pn.x, pW = sel ? pm.y : pm.x;
-                    double pN, pS, pp;
-                    if (sel == 0) { pS = pc.y; pN = sp[idx - 1]; pp = pc.x; }
-                    else          { pN = pc.x; pS = sp[idx + 1]; pp = pc.y; }
-                    const double t = fma(k.rdx2, pE + pW, fma(k.rdy2, pS + pN, -sr[idx]));
-                    const double rr = fma(-k.diag, pp, t);
-                    acc = fma(rr, rr, acc);
-                }
-            }
-            {
-                const int bsel = sel ^ 1;  // the black cell: only if it was not swept
-                const int idx = r * TW + c.col0 + bsel;
-                if ((all_black || sf[idx] != CF_FLUID) && interior(c, gx, c.gy0 + bsel)) {
-                    const double pE = bsel ? pn.y : pn.x, pW = bsel ? pm.y : pm.x;
-                    double pN, pS, pp;
-                    if (bsel == 0) { pS = pc.y; pN = sp[idx - 1]; pp = pc.x; }
-                    else           { pN = pc.x; pS = sp[idx + 1]; pp = pc.y; }
-                    const double t = fma(k.rdx2, pE + pW, fma(k.rdy2, pS + pN, -sr[idx]));
-                    const double rr = fma(-k.diag, pp, t);
-                    acc = fma(rr, rr, acc);
-                }
+// explicit residuals of the cells in `mask` (current field) into acc
+__device__ __forceinline__ void explicit_norm(const double2 (&P)[RPT], const double *sp,
+                                              const double *sr, int base, int r_begin,
+                                              uint32_t mask, const RbConsts &k, double &acc) {
+    if (mask == 0) return;
+    const double2 up = r_begin > 0 ? lds2(sp, base - TW) : make_double2(0.0, 0.0);
+    const double2 dn = r_begin + RPT < TXR ? lds2(sp, base + RPT * TW) : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < RPT; i++) {
+#pragma unroll
+        for (int sel = 0; sel < 2; sel++) {
+            if (mask & (1u << (2 * i + sel))) {
+                SB_T_OF_CELL(i, sel)
+                const double rr = fma(-k.diag, sel ? P[i].y : P[i].x, t_);
+                acc = fma(rr, rr, acc);
             }
         }
-        pm = pc;
-        pc = pn;
     }
 }
 
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int PAR>
 __global__ void __launch_bounds__(NTHR, 2)
 sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__ CUtensorMap tm_p1,
               const __grid_constant__ CUtensorMap tm_rhs, const uint8_t *__restrict__ cflag,
@@ -209,22 +213,21 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
               int norm_only) {
     // norm_only: no sweeps, no write-back; partial[tile] = sum of squared residuals of the
     // current field (calculate_norm_squared on its own, src/simulation.rs:216-227)
-    const int T = norm_only ? 1 : ctl->active_T;
-    if (T == 0) return;
+    const int T = norm_only ? 0 : ctl->active_T;
+    if (!norm_only && T == 0) return;
     const int src = ctl->src;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sp = reinterpret_cast<double *>(smem_raw);
     double *sr = sp + TILE;
-    uint8_t *sf = reinterpret_cast<uint8_t *>(sr + TILE);
+    uint8_t *sf = reinterpret_cast<uint8_t *>(sr + TILE);   // edge class of BC cells
     uint64_t *bar = reinterpret_cast<uint64_t *>(sf + TILE);
-    double *sred = reinterpret_cast<double *>(sf + TILE + 64);
+    double *sred = reinterpret_cast<double *>(sf + TILE + 64);  // [TMAX][NWARP]
 
-    const int hy = h;  // h is even, so the owned columns start 16-byte aligned
-    const int BX = TXR - 2 * h, BY = TW - 2 * hy;
+    const int BX = TXR - 2 * h, BY = TW - 2 * h;  // h is even: owned columns 16-byte aligned
     const int tile_i = blockIdx.x / tiles_y, tile_j = blockIdx.x - tile_i * tiles_y;
-    const int tx0 = tile_i * BX - h;    // local row of tile row 0
-    const int ty0 = tile_j * BY - hy;   // column of tile column 0
+    const int tx0 = tile_i * BX - h;   // local row of tile row 0 (even)
+    const int ty0 = tile_j * BY - h;   // column of tile column 0 (even)
 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -238,87 +241,173 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
         tma_load_2d(sr, &tm_rhs, ty0, tx0, bar);
     }
 
-    TileCtx c;
     const int tc = threadIdx.x % TCOLS, tr = threadIdx.x / TCOLS;
-    c.r_begin = tr * RPT;
-    c.col0 = 2 * tc;
-    c.gx_base = g.gx0 + tx0;
-    c.gy0 = (int64_t)ty0 + c.col0;
-    c.NX = g.NX;
-    c.NY = g.NY;
-    c.own_gx0 = g.gx0 + g.own0;
-    c.own_gx1 = g.gx0 + g.own1;
-    c.h = h;
-    c.hy = hy;
-    double acc[TMAX];
-#pragma unroll
-    for (int i = 0; i < TMAX; i++) acc[i] = 0.0;
+    const int r_begin = tr * RPT, col0 = 2 * tc;
+    const int base = r_begin * TW + col0;
+    const int gy0 = ty0 + col0;  // global column of the thread's first cell (even)
 
-    // cell flags of this thread's own cells (nobody else reads them): global -> smem
-    for (int r = c.r_begin; r < c.r_begin + RPT; r++) {
-        const int64_t lx = (int64_t)tx0 + r;
-        uint16_t ff = 0;
-        if (lx >= 0 && lx < g.nxl && c.gy0 >= 0 && c.gy0 + 1 < g.pitch)
-            ff = *reinterpret_cast<const uint16_t *>(cflag + lx * g.pitch + c.gy0);
-        *reinterpret_cast<uint16_t *>(sf + r * TW + c.col0) = ff;
+    // ---- cell flags of this thread's 2 x RPT cells -> bit masks (while the TMA flies) ----
+    // Geometry first (32-bit, mostly uniform per thread row): which of the thread's rows /
+    // columns are swept, counted, BC-able, stored.  Then one 16-bit flag load per row.
+    Masks m;
+    uint32_t m_store;  // rows (bit 2i) this thread writes back
+    {
+        const int nxl = (int)g.nxl, NYi = (int)g.NY;
+        // tile-row ranges [lo, hi): rows present in this slab / interior rows of the grid /
+        // rows owned by this slab
+        const int in_lo = max(0, -tx0), in_hi = min(TXR, nxl - tx0);
+        const int64_t gxt = g.gx0 + tx0;  // global x of tile row 0
+        const int int_lo = (int)max((int64_t)0, 1 - gxt);
+        const int int_hi = (int)max((int64_t)0, min((int64_t)TXR, g.NX - 1 - gxt));
+        const int own_lo = max(0, (int)g.own0 - tx0), own_hi = min(TXR, (int)g.own1 - tx0);
+        const uint32_t rows_upd = row_bits(max(int_lo, 1), min(int_hi, TXR - 1), r_begin);
+        const uint32_t rows_cnt =
+            row_bits(max(max(int_lo, own_lo), h), min(min(int_hi, own_hi), TXR - h), r_begin);
+        const uint32_t rows_bc = row_bits(max(in_lo, 1), min(in_hi, TXR - 1), r_begin);
+        const uint32_t rows_st = row_bits(max(in_lo, h), min(in_hi, TXR - h), r_begin);
+        // column properties of the two cells -> 0x555555 / 0xAAAAAA patterns
+        uint32_t cols_upd = 0, cols_cnt = 0, cols_bc = 0;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int col = col0 + e, gy = gy0 + e;
+            const uint32_t pat = 0x55555555u << e;
+            const bool interior = gy >= 1 && gy <= NYi - 2;
+            const bool tile_col = col >= 1 && col <= TW - 2;
+            if (interior && tile_col) cols_upd |= pat;
+            if (interior && col >= h && col < TW - h) cols_cnt |= pat;
+            if (tile_col) cols_bc |= pat;
+        }
+        const bool col_in = gy0 >= 0 && gy0 + 1 < (int)g.pitch;
+        const uint8_t *fp = cflag + (int64_t)(tx0 + r_begin) * g.pitch + gy0;
+        uint16_t ff[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; i++) {
+            const int r = r_begin + i;
+            ff[i] = 0;
+            if (col_in && r >= in_lo && r < in_hi)
+                ff[i] = *reinterpret_cast<const uint16_t *>(fp + (int64_t)i * g.pitch);
+        }
+        uint32_t f_valid = 0, f_fluid = 0, f_near = 0, f_edge = 0;
+#pragma unroll
+        for (int i = 0; i < RPT; i++) {
+            const uint32_t w = ff[i];
+            // per byte: valid = bit 7, fluid = (b & 0x87) == 0x80, near = bit 3, edge = bits 3-6
+            const uint32_t valid = ((w >> 7) & 1u) | ((w >> 14) & 2u);
+            const uint32_t kindz = (((w & 0x0007u) == 0) ? 1u : 0u) | (((w & 0x0700u) == 0) ? 2u : 0u);
+            const uint32_t fluid = valid & kindz;
+            const uint32_t near = ((w >> 3) & 1u) | ((w >> 10) & 2u);
+            const uint32_t edge = (((w & 0x0078u) != 0) ? 1u : 0u) | (((w & 0x7800u) != 0) ? 2u : 0u);
+            f_valid |= valid << (2 * i);
+            f_fluid |= fluid << (2 * i);
+            f_near |= (near & fluid) << (2 * i);
+            f_edge |= (edge & valid & ~fluid) << (2 * i);
+        }
+        m.upd = f_fluid & rows_upd & cols_upd;
+        m.cnt = f_valid & rows_cnt & cols_cnt;
+        // explicit residual: non-fluid cells, and red fluid cells next to a non-fluid cell
+        // (CF_NEAR); black fluid cells never need it
+        m.exp_ = m.cnt & (~f_fluid | (f_near & red_mask<PAR>()));
+        m.bc = f_edge & rows_bc & cols_bc;
+        m_store = rows_st & 0x55555555u;
+        if (m.bc) {  // edge classes of the BC cells, for bc_value()
+#pragma unroll
+            for (int i = 0; i < RPT; i++) {
+                if ((m.bc >> (2 * i)) & 3u) {
+                    const uint32_t w = ff[i];
+                    const uint16_t edges = (uint16_t)(((w >> 3) & 0x0Fu) | (((w >> 11) & 0x0Fu) << 8));
+                    *reinterpret_cast<uint16_t *>(sf + (r_begin + i) * TW + col0) = edges;
+                }
+            }
+        }
     }
+    // block-uniform: does any thread have BC cells / explicit-residual cells?
+    const int has_bc = __syncthreads_or(m.bc != 0);
+    const int has_exp = __syncthreads_or(m.exp_ != 0);
+    const uint32_t m_red = red_mask<PAR>();
+    const uint32_t m_lag_all = m.cnt & m_red & ~m.exp_;  // red residuals taken one sweep late
 
     mbar_wait(bar, 0);
 
+    // own pressures -> registers, for the whole pass
+    double2 P[RPT];
 #pragma unroll
-    for (int it = 0; it < TMAX; it++) {
-        if (it < T && !norm_only) {
-            // pressure BC: boundary cells take the (average of the) fluid neighbour(s)
-            {
-                int r0 = max(c.r_begin, 1), r1 = min(c.r_begin + RPT, TXR - 1);
-                for (int r = r0; r < r1; r++) {
-                    const int idx = r * TW + c.col0;
-                    const uint16_t ff = *reinterpret_cast<const uint16_t *>(sf + idx);
-                    if ((ff & 0x7878) == 0) continue;
-                    const int e0 = (ff >> 3) & 15, e1 = (ff >> 11) & 15;
-                    if (e0 && c.col0 >= 1) bc_cell(sp, idx, e0);
-                    if (e1 && c.col0 + 1 <= TW - 2) bc_cell(sp, idx + 1, e1);
+    for (int i = 0; i < RPT; i++) P[i] = lds2(sp, base + i * TW);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc_prev = 0.0, acc_cur = 0.0;
+
+    if (norm_only) {
+        explicit_norm(P, sp, sr, base, r_begin, m.cnt, k, acc_cur);
+        const double v = warp_sum(acc_cur);
+        if (lane == 0) sred[warp] = v;
+    }
+
+    for (int it = 0; it < T; it++) {
+        // pressure BC: boundary cells take the (average of the) fluid neighbour(s)
+        if (has_bc) {
+            if (m.bc) {
+#pragma unroll
+                for (int i = 0; i < RPT; i++) {
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        if (m.bc & (1u << (2 * i + e))) {
+                            const int idx = base + i * TW + e;
+                            const double v = bc_value(sp, idx, sf[idx]);
+                            sp[idx] = v;
+                            if (e) P[i].y = v; else P[i].x = v;
+                        }
+                    }
                 }
             }
             __syncthreads();
-            half_sweep<0>(sp, sr, sf, c, k, acc[it]);
-            __syncthreads();
-            half_sweep<1>(sp, sr, sf, c, k, acc[it]);
-            __syncthreads();
-            norm_rest(sp, sr, sf, c, k, acc[it], false);
-            __syncthreads();
         }
+        half_sweep<PAR, 0>(P, sp, sr, base, r_begin, m, it > 0 ? m_lag_all : 0u, k, acc_prev,
+                           acc_cur);
+        if (it > 0) {  // sweep it-1 is now complete in acc_prev
+            const double v = warp_sum(acc_prev);
+            if (lane == 0) sred[(it - 1) * NWARP + warp] = v;
+        }
+        __syncthreads();
+        acc_prev = 0.0;
+        half_sweep<PAR, 1>(P, sp, sr, base, r_begin, m, 0u, k, acc_prev, acc_cur);
+        __syncthreads();
+        // explicit residuals of this sweep: the rare cells every sweep, all red cells after
+        // the last sweep of the pass
+        const bool last = it == T - 1;
+        if (has_exp || last) {
+            explicit_norm(P, sp, sr, base, r_begin, last ? (m.exp_ | (m.cnt & m_red)) : m.exp_, k,
+                          acc_cur);
+            // before the next BC / red half-sweep overwrites cells these residuals read
+            if (!last) __syncthreads();
+        }
+        acc_prev = acc_cur;
+        acc_cur = 0.0;
     }
-    if (norm_only) norm_rest(sp, sr, sf, c, k, acc[0], true);
+    if (T > 0) {
+        const double v = warp_sum(acc_prev);
+        if (lane == 0) sred[(T - 1) * NWARP + warp] = v;
+    }
 
-    // write the exact inner region to the other buffer
-    if (!norm_only) {
-        double *pout = pbuf[src ^ 1];
-        int r0 = max(c.r_begin, h), r1 = min(c.r_begin + RPT, TXR - h);
-        if (c.col0 >= hy && c.col0 < TW - hy && c.gy0 < g.NY) {
-            for (int r = r0; r < r1; r++) {
-                const int64_t lx = (int64_t)tx0 + r;
-                if (lx < 0 || lx >= g.nxl) continue;
-                const double2 val = lds2(sp, r * TW + c.col0);
-                double *dst = pout + lx * g.pitch + c.gy0;
-                if (c.gy0 + 1 < g.NY) *reinterpret_cast<double2 *>(dst) = val;
-                else dst[0] = val.x;
+    // write the exact inner region to the other buffer, straight from registers
+    if (!norm_only && m_store && col0 >= h && col0 < TW - h && gy0 < (int)g.NY) {
+        double *pout = pbuf[src ^ 1] + (int64_t)(tx0 + r_begin) * g.pitch + gy0;
+        const bool pair = gy0 + 1 < (int)g.NY;
+#pragma unroll
+        for (int i = 0; i < RPT; i++) {
+            if (m_store & (1u << (2 * i))) {
+                double *dst = pout + (int64_t)i * g.pitch;
+                if (pair) *reinterpret_cast<double2 *>(dst) = P[i];
+                else dst[0] = P[i].x;
             }
         }
     }
 
-    // block-reduce the per-sweep residual sums (fixed tree => deterministic)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int it = 0; it < TMAX; it++) {
-        double v = acc[it];
-        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) sred[warp * TMAX + it] = v;
-    }
+    // per-sweep residual sums of the tile (fixed order => deterministic)
     __syncthreads();
-    if (threadIdx.x < TMAX && (int)threadIdx.x < T) {
+    const int levels = norm_only ? 1 : T;
+    if ((int)threadIdx.x < levels) {
         double tsum = 0.0;
-        for (int w = 0; w < NTHR / 32; w++) tsum += sred[w * TMAX + threadIdx.x];
+        for (int w = 0; w < NWARP; w++) tsum += sred[threadIdx.x * NWARP + w];
         partial[(int64_t)threadIdx.x * ntiles + blockIdx.x] = tsum;
     }
 }
@@ -359,7 +448,9 @@ sb_status ensure_tmaps(sb_sim *s) {
         if ((st = make_map(fn, &s->tm_p[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, s->p[i], s->g)))
             return st;
     if ((st = make_map(fn, &s->tm_rhs, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, s->rhs, s->g))) return st;
-    SB_CUDA(cudaFuncSetAttribute(sor_rb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SB_CUDA(cudaFuncSetAttribute(sor_rb_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)SMEM_BYTES));
+    SB_CUDA(cudaFuncSetAttribute(sor_rb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)SMEM_BYTES));
     s->tmaps_ready = true;
     return SB_OK;
@@ -398,9 +489,19 @@ sb_status launch_sor_rb_pass(sb_sim *s, int *ntiles_out, int norm_only) {
     k.diag = (2.0 * k.rdx2) + (2.0 * k.rdy2);
     k.mid = s->prm.omega / ((2.0 / dx2) + (2.0 / dy2));
     k.omw = 1.0 - s->prm.omega;
-    sor_rb_kernel<<<ntiles, NTHR, SMEM_BYTES, s->stream>>>(s->tm_p[0], s->tm_p[1], s->tm_rhs,
-                                                          s->cflag, g, pbuf_ptr(s), s->d_ctl,
-                                                          s->d_partial, tiles_y, ntiles, h, k, norm_only);
+    // tile row 0 is local row -h (even offset): the colour of the thread's first row follows
+    // the parity of the slab's global row offset
+    const int par = (int)(((g.gx0 % 2) + 2) % 2);
+    if (!norm_only) prof_mark(s);
+    if (par)
+        sor_rb_kernel<1><<<ntiles, NTHR, SMEM_BYTES, s->stream>>>(
+            s->tm_p[0], s->tm_p[1], s->tm_rhs, s->cflag, g, pbuf_ptr(s), s->d_ctl, s->d_partial,
+            tiles_y, ntiles, h, k, norm_only);
+    else
+        sor_rb_kernel<0><<<ntiles, NTHR, SMEM_BYTES, s->stream>>>(
+            s->tm_p[0], s->tm_p[1], s->tm_rhs, s->cflag, g, pbuf_ptr(s), s->d_ctl, s->d_partial,
+            tiles_y, ntiles, h, k, norm_only);
+    if (!norm_only) prof_mark(s);
     s->launches++;
     SB_CUDA(cudaGetLastError());
     *ntiles_out = ntiles;

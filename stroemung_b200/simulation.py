@@ -312,6 +312,25 @@ class Simulation:
     def kernel_launches(self):
         return int(_capi.lib().sb_kernel_launches(self._h))
 
+    def timer_begin(self):
+        self._check(_capi.lib().sb_timer_begin(self._h))
+
+    def timer_end(self):
+        """device time (ms, CUDA events on the handle's stream) since timer_begin"""
+        ms = C.c_double()
+        self._check(_capi.lib().sb_timer_end(self._h, C.byref(ms)))
+        return ms.value
+
+    def profile_enable(self, enable=True):
+        self._check(_capi.lib().sb_profile_enable(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """durations (ms) of the SOR sweep-kernel launches since the last read"""
+        buf = np.zeros(4096)
+        n = C.c_size_t()
+        self._check(_capi.lib().sb_profile_read(self._h, _dp(buf), buf.size, C.byref(n)))
+        return buf[:min(n.value, buf.size)].copy()
+
     @property
     def last_sor_ms(self):
         return float(_capi.lib().sb_last_sor_ms(self._h))

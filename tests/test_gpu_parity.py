@@ -320,19 +320,25 @@ def test_red_black_early_exit_inside_block(T):
 @pytest.mark.parametrize("eps", [1e-3, 1e-6])
 def test_red_black_vs_reference_order_converged(eps):
     """Performance mode against the REFERENCE ordering (SURVEY.md 8a A6 protocol): compare
-    on converged ticks, pressure up to its free constant.  Both solvers stop once their
-    residual norm is below eps, so their fields agree to a small multiple of eps
-    (measured on the B200: 1.3 eps on u at eps = 1e-3); the tolerance is 3 eps."""
+    on converged ticks, pressure up to its free constant.  Both orderings are started from
+    the same converged state (250 reference-order ticks of the channel; before that SOR hits
+    its cap every tick and the two orderings legitimately drift apart), run 10 more ticks and
+    must agree to a small multiple of the SOR epsilon -- each stops at a residual norm < eps.
+    Measured on the B200: 1.3 eps on u at eps = 1e-3; the tolerance is 3 eps."""
     shape = (34, 18)
     g = presets.simple_inflow(shape)
-    unf = unfinalized(shape[0], shape[1], g["kind"], g["bu"], g["bv"],
-                      sor_absolute_epsilon=eps, max_iterations=2000)
+    warm = Simulation.try_from(unfinalized(shape[0], shape[1], g["kind"], g["bu"], g["bv"]))
+    warm.run_ticks(250)
+    assert warm.run_simulation_tick()[0] < 100  # converged regime reached
+    unf = unfinalized(shape[0], shape[1], g["kind"], g["bu"], g["bv"], p=warm.grid.pressure,
+                      u=warm.grid.u, v=warm.grid.v, sor_absolute_epsilon=eps,
+                      max_iterations=5000, initial_norm_squared=0.0)
     rb = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK, temporal_block=2)
     lex = Simulation.try_from(unf, sor_mode=SOR_REFERENCE_ORDER)
-    for t in range(300):
-        it_rb, _ = rb.run_simulation_tick()
-        it_lex, _ = lex.run_simulation_tick()
-    assert it_rb < 2000 and it_lex < 2000  # both in the converged regime
+    for t in range(10):
+        it_rb, n_rb = rb.run_simulation_tick()
+        it_lex, n_lex = lex.run_simulation_tick()
+        assert it_rb < 5000 and it_lex < 5000 and n_rb < eps * eps and n_lex < eps * eps
     fluid = g["kind"] == 0
     du = np.abs(rb.grid.u - lex.grid.u)[fluid].max()
     dv = np.abs(rb.grid.v - lex.grid.v)[fluid].max()
