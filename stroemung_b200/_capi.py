@@ -6,8 +6,11 @@ no CPU fallback in the product path.
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _DIR = Path(__file__).resolve().parent
-LIB_PATH = _DIR / "libstroemung_b200.so"
+# SB_LIB selects another build of the same library (kernel-variant experiments)
+LIB_PATH = Path(os.environ.get("SB_LIB", _DIR / "libstroemung_b200.so"))
 
 (SB_OK, SB_BOUNDARY_TOO_THIN, SB_BOUNDARY_LIST_INCORRECT, SB_CUDA_ERROR,
  SB_INVALID_ARGUMENT) = range(5)

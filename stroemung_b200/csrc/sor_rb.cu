@@ -16,6 +16,12 @@
 // half-sweep) and the rhs reads.  Row parity is a template parameter and the row loops are
 // fully unrolled, so which cell of a pair has which colour is known at compile time.
 //
+// Shared-memory layout: after the TMA has landed a tile in natural order, every warp
+// re-lays its 64-column half rows in place as [32 first cells | 32 second cells] of its 32
+// column pairs.  Each lane then reads / writes single doubles at an 8-byte stride across
+// the warp: the neighbour, rhs and store accesses of a half-sweep are bank-conflict free
+// (in natural order every one of them is a 2-way conflict: 8 bytes at a 16-byte stride).
+//
 // Halo: the tile carries h = 2T+2 cells.  Boundary cells on the outermost tile ring cannot
 // take their pressure BC (their fluid neighbour may lie outside the tile), so after sweep k
 // the fluid values at distance >= 2k+1 from the tile edge are exact; T sweeps leave the
@@ -46,14 +52,18 @@ namespace {
 
 constexpr int TXR = 48;                 // tile rows
 constexpr int TW = 128;                 // tile columns
-constexpr int NTHR = 256;
+#ifndef SB_RB_NTHR
+#define SB_RB_NTHR 256
+#endif
+constexpr int NTHR = SB_RB_NTHR;
 constexpr int TCOLS = TW / 2;           // thread columns (2 cells each)
 constexpr int TROWS = NTHR / TCOLS;     // thread rows
 constexpr int RPT = TXR / TROWS;        // rows per thread
 constexpr int TMAX = 4;
 constexpr int TILE = TXR * TW;
 constexpr int NWARP = NTHR / 32;
-constexpr size_t SMEM_BYTES = (size_t)TILE * 17 + 64 + NWARP * TMAX * sizeof(double);
+constexpr int SMEM_PAD = 128;  // in front of the p tile: the ring cells' out-of-tile reads
+constexpr size_t SMEM_BYTES = SMEM_PAD + (size_t)TILE * 17 + 64 + NWARP * TMAX * sizeof(double);
 static_assert(TXR % TROWS == 0 && RPT % 2 == 0, "rows must split evenly, even per thread");
 static_assert(2 * RPT <= 32, "cell masks are 32-bit");
 
@@ -100,19 +110,40 @@ __device__ __forceinline__ double2 lds2(const double *sp, int idx) {
     return *reinterpret_cast<const double2 *>(sp + idx);
 }
 
+// index of tile cell (r, col) in the split layout: pair t = col/2 sits in the 64-wide half
+// row t/32, at lane t%32 of its first-cell or second-cell block
+__device__ __forceinline__ int cidx(int r, int col) {
+    const int t = col >> 1;
+    return r * TW + ((t >> 5) << 6) + ((col & 1) << 5) + (t & 31);
+}
+
 // pressure BC of one boundary cell from its fluid neighbours (src/grid/mod.rs:351-399)
-__device__ __forceinline__ double bc_value(const double *sp, int idx, int edge) {
+__device__ __forceinline__ double bc_value(const double *sp, int r, int col, int edge) {
+    const double n = sp[cidx(r, col - 1)], s = sp[cidx(r, col + 1)];
+    const double e = sp[cidx(r + 1, col)], w = sp[cidx(r - 1, col)];
     switch (edge) {
-    case SB_EDGE_N: return sp[idx - 1];
-    case SB_EDGE_NE: return (sp[idx - 1] + sp[idx + TW]) / 2.0;
-    case SB_EDGE_E: return sp[idx + TW];
-    case SB_EDGE_SE: return (sp[idx + 1] + sp[idx + TW]) / 2.0;
-    case SB_EDGE_S: return sp[idx + 1];
-    case SB_EDGE_SW: return (sp[idx + 1] + sp[idx - TW]) / 2.0;
-    case SB_EDGE_W: return sp[idx - TW];
-    case SB_EDGE_NW: return (sp[idx - 1] + sp[idx - TW]) / 2.0;
-    default: return sp[idx];
+    case SB_EDGE_N: return n;
+    case SB_EDGE_NE: return (n + e) / 2.0;
+    case SB_EDGE_E: return e;
+    case SB_EDGE_SE: return (s + e) / 2.0;
+    case SB_EDGE_S: return s;
+    case SB_EDGE_SW: return (s + w) / 2.0;
+    case SB_EDGE_W: return w;
+    case SB_EDGE_NW: return (n + w) / 2.0;
+    default: return sp[cidx(r, col)];
     }
+}
+
+// where a thread's cells live in the split layout
+struct Thr {
+    int bx;    // index of the first cell of the thread's pair in its first row
+    int offL;  // from there to the left foreign neighbour (second cell of the pair before)
+    int offR;  // ... to the right foreign neighbour (first cell of the pair after)
+    int r_begin;
+};
+
+__device__ __forceinline__ double2 lds_pair(const double *sp, int bx) {
+    return make_double2(sp[bx], sp[bx + 32]);
 }
 
 // both cell bits of the thread's rows i with r_begin + i in [lo, hi)
@@ -124,7 +155,7 @@ __device__ __forceinline__ uint32_t row_bits(int lo, int hi, int r_begin) {
 
 // per-thread cell masks; bit 2*i + e is cell (row r_begin + i, column col0 + e)
 struct Masks {
-    uint32_t upd;   // fluid, interior of the grid, not on the tile ring: swept
+    uint32_t upd;   // fluid and interior of the grid: swept
     uint32_t cnt;   // in the tile's exact inner region, interior, owned: counts in the norm
     uint32_t exp_;  // counted cells whose residual needs an explicit evaluation every sweep
     uint32_t bc;    // boundary cells with an edge class, not on the tile ring: take the BC
@@ -142,21 +173,78 @@ __host__ __device__ constexpr uint32_t red_mask() {
 #define SB_T_OF_CELL(i, sel)                                                            \
     const double2 &Pm_ = (i) == 0 ? up : P[(i) == 0 ? 0 : (i)-1];                       \
     const double2 &Pn_ = (i) == RPT - 1 ? dn : P[(i) == RPT - 1 ? RPT - 1 : (i) + 1];   \
-    const int idx_ = base + (i)*TW + (sel);                                             \
+    const int bx_ = th.bx + (i)*TW;                                                     \
     const double pE_ = (sel) ? Pn_.y : Pn_.x, pW_ = (sel) ? Pm_.y : Pm_.x;              \
-    const double pS_ = (sel) ? sp[idx_ + 1] : P[i].y;                                   \
-    const double pN_ = (sel) ? P[i].x : sp[idx_ - 1];                                   \
-    const double t_ = fma(k.rdx2, pE_ + pW_, fma(k.rdy2, pS_ + pN_, -sr[idx_]));
+    const double pS_ = (sel) ? sp[bx_ + th.offR] : P[i].y;                              \
+    const double pN_ = (sel) ? P[i].x : sp[bx_ + th.offL];                              \
+    const double t_ = fma(k.rdx2, pE_ + pW_, fma(k.rdy2, pS_ + pN_, -sr[bx_ + (sel)*32]));
+
+// bits of the cells with colour COLOUR when the thread's first row has parity PAR
+template <int PAR, int COLOUR>
+__host__ __device__ constexpr uint32_t colour_mask() {
+    uint32_t m = 0;
+    for (int i = 0; i < RPT; i++) m |= 1u << (2 * i + ((PAR ^ i ^ COLOUR) & 1));
+    return m;
+}
 
 // one colour of one sweep.  COLOUR 0 (red): cells in m_lag also contribute the residual of
 // the PREVIOUS sweep to acc_prev.  COLOUR 1 (black): counted cells contribute this sweep's
 // residual to acc_cur.
+//
+// Two code paths, chosen per warp.  Fast path: every lane sweeps all its cells of the colour
+// (the common case away from walls and obstacles) -- straight-line code, loads of GROUP rows
+// issued ahead of the arithmetic, so the rows' independent dependency chains (LDS ->
+// DADD -> 3 DFMA -> STS, ~60 cycles each) overlap.  Slow path: one branch per cell.
+// Cells on the tile ring are swept like any other: their out-of-tile neighbour reads land in
+// the padding / adjacent row of the shared-memory tile and only produce values inside the
+// (already inexact) halo.
 template <int PAR, int COLOUR>
 __device__ __forceinline__ void half_sweep(double2 (&P)[RPT], double *sp, const double *sr,
-                                           int base, int r_begin, const Masks &m, uint32_t m_lag,
+                                           const Thr &th, const Masks &m, uint32_t m_lag,
                                            const RbConsts &k, double &acc_prev, double &acc_cur) {
-    const double2 up = r_begin > 0 ? lds2(sp, base - TW) : make_double2(0.0, 0.0);
-    const double2 dn = r_begin + RPT < TXR ? lds2(sp, base + RPT * TW) : make_double2(0.0, 0.0);
+    const double2 up = th.r_begin > 0 ? lds_pair(sp, th.bx - TW) : make_double2(0.0, 0.0);
+    const double2 dn =
+        th.r_begin + RPT < TXR ? lds_pair(sp, th.bx + RPT * TW) : make_double2(0.0, 0.0);
+    constexpr uint32_t cm = colour_mask<PAR, COLOUR>();
+    if (__all_sync(0xffffffffu, (m.upd & cm) == cm)) {
+        constexpr int GROUP = RPT % 4 == 0 ? 4 : 3;
+#pragma unroll
+        for (int g0 = 0; g0 < RPT; g0 += GROUP) {
+            double fo[GROUP], rh[GROUP];
+#pragma unroll
+            for (int j = 0; j < GROUP; j++) {
+                const int i = g0 + j;
+                const int sel = (PAR ^ i ^ COLOUR) & 1;
+                fo[j] = sp[th.bx + i * TW + (sel ? th.offR : th.offL)];
+                rh[j] = sr[th.bx + i * TW + sel * 32];
+            }
+#pragma unroll
+            for (int j = 0; j < GROUP; j++) {
+                const int i = g0 + j;
+                const int sel = (PAR ^ i ^ COLOUR) & 1;
+                const uint32_t bit = 1u << (2 * i + sel);
+                const double2 &Pm = i == 0 ? up : P[i == 0 ? 0 : i - 1];
+                const double2 &Pn = i == RPT - 1 ? dn : P[i == RPT - 1 ? RPT - 1 : i + 1];
+                const double pE = sel ? Pn.y : Pn.x, pW = sel ? Pm.y : Pm.x;
+                const double pS = sel ? fo[j] : P[i].y;
+                const double pN = sel ? P[i].x : fo[j];
+                const double pold = sel ? P[i].y : P[i].x;
+                const double t = fma(k.rdx2, pE + pW, fma(k.rdy2, pS + pN, -rh[j]));
+                if (COLOUR == 0) {
+                    const double rr = fma(-k.diag, pold, t);
+                    if (m_lag & bit) acc_prev = fma(rr, rr, acc_prev);
+                }
+                const double pnew = fma(k.mid, t, k.omw * pold);
+                if (sel) P[i].y = pnew; else P[i].x = pnew;
+                sp[th.bx + i * TW + sel * 32] = pnew;
+                if (COLOUR == 1) {
+                    const double rr = fma(-k.diag, pnew, t);
+                    if (m.cnt & bit) acc_cur = fma(rr, rr, acc_cur);
+                }
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < RPT; i++) {
         const int sel = (PAR ^ i ^ COLOUR) & 1;
@@ -170,7 +258,7 @@ __device__ __forceinline__ void half_sweep(double2 (&P)[RPT], double *sp, const 
             }
             const double pnew = fma(k.mid, t_, k.omw * pold);
             if (sel) P[i].y = pnew; else P[i].x = pnew;
-            sp[idx_] = pnew;
+            sp[bx_ + sel * 32] = pnew;
             if (COLOUR == 1 && (m.cnt & bit)) {
                 const double rr = fma(-k.diag, pnew, t_);
                 acc_cur = fma(rr, rr, acc_cur);
@@ -179,13 +267,51 @@ __device__ __forceinline__ void half_sweep(double2 (&P)[RPT], double *sp, const 
     }
 }
 
-// explicit residuals of the cells in `mask` (current field) into acc
+// explicit residuals of the cells in `mask` (current field) into acc.  `uniform_red`: the
+// caller asks for all counted red cells (last sweep of a pass); if the whole warp sweeps all
+// its red cells the straight-line path is taken.
+template <int PAR>
 __device__ __forceinline__ void explicit_norm(const double2 (&P)[RPT], const double *sp,
-                                              const double *sr, int base, int r_begin,
-                                              uint32_t mask, const RbConsts &k, double &acc) {
+                                              const double *sr, const Thr &th, uint32_t mask,
+                                              uint32_t m_upd, bool uniform_red,
+                                              const RbConsts &k, double &acc) {
+    constexpr uint32_t cm = colour_mask<PAR, 0>();
+    const bool fast = uniform_red && (m_upd & cm) == cm && (mask & ~cm) == 0;
+    if (__all_sync(0xffffffffu, fast)) {
+        const double2 up = th.r_begin > 0 ? lds_pair(sp, th.bx - TW) : make_double2(0.0, 0.0);
+        const double2 dn =
+            th.r_begin + RPT < TXR ? lds_pair(sp, th.bx + RPT * TW) : make_double2(0.0, 0.0);
+        constexpr int GROUP = RPT % 4 == 0 ? 4 : 3;
+#pragma unroll
+        for (int g0 = 0; g0 < RPT; g0 += GROUP) {
+            double fo[GROUP], rh[GROUP];
+#pragma unroll
+            for (int j = 0; j < GROUP; j++) {
+                const int i = g0 + j;
+                const int sel = (PAR ^ i) & 1;
+                fo[j] = sp[th.bx + i * TW + (sel ? th.offR : th.offL)];
+                rh[j] = sr[th.bx + i * TW + sel * 32];
+            }
+#pragma unroll
+            for (int j = 0; j < GROUP; j++) {
+                const int i = g0 + j;
+                const int sel = (PAR ^ i) & 1;
+                const double2 &Pm = i == 0 ? up : P[i == 0 ? 0 : i - 1];
+                const double2 &Pn = i == RPT - 1 ? dn : P[i == RPT - 1 ? RPT - 1 : i + 1];
+                const double pE = sel ? Pn.y : Pn.x, pW = sel ? Pm.y : Pm.x;
+                const double pS = sel ? fo[j] : P[i].y;
+                const double pN = sel ? P[i].x : fo[j];
+                const double t = fma(k.rdx2, pE + pW, fma(k.rdy2, pS + pN, -rh[j]));
+                const double rr = fma(-k.diag, sel ? P[i].y : P[i].x, t);
+                if (mask & (1u << (2 * i + sel))) acc = fma(rr, rr, acc);
+            }
+        }
+        return;
+    }
     if (mask == 0) return;
-    const double2 up = r_begin > 0 ? lds2(sp, base - TW) : make_double2(0.0, 0.0);
-    const double2 dn = r_begin + RPT < TXR ? lds2(sp, base + RPT * TW) : make_double2(0.0, 0.0);
+    const double2 up = th.r_begin > 0 ? lds_pair(sp, th.bx - TW) : make_double2(0.0, 0.0);
+    const double2 dn =
+        th.r_begin + RPT < TXR ? lds_pair(sp, th.bx + RPT * TW) : make_double2(0.0, 0.0);
 #pragma unroll
     for (int i = 0; i < RPT; i++) {
 #pragma unroll
@@ -218,7 +344,7 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
     const int src = ctl->src;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *sp = reinterpret_cast<double *>(smem_raw);
+    double *sp = reinterpret_cast<double *>(smem_raw + SMEM_PAD);
     double *sr = sp + TILE;
     uint8_t *sf = reinterpret_cast<uint8_t *>(sr + TILE);   // edge class of BC cells
     uint64_t *bar = reinterpret_cast<uint64_t *>(sf + TILE);
@@ -260,7 +386,7 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
         const int int_lo = (int)max((int64_t)0, 1 - gxt);
         const int int_hi = (int)max((int64_t)0, min((int64_t)TXR, g.NX - 1 - gxt));
         const int own_lo = max(0, (int)g.own0 - tx0), own_hi = min(TXR, (int)g.own1 - tx0);
-        const uint32_t rows_upd = row_bits(max(int_lo, 1), min(int_hi, TXR - 1), r_begin);
+        const uint32_t rows_upd = row_bits(int_lo, int_hi, r_begin);
         const uint32_t rows_cnt =
             row_bits(max(max(int_lo, own_lo), h), min(min(int_hi, own_hi), TXR - h), r_begin);
         const uint32_t rows_bc = row_bits(max(in_lo, 1), min(in_hi, TXR - 1), r_begin);
@@ -273,7 +399,7 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
             const uint32_t pat = 0x55555555u << e;
             const bool interior = gy >= 1 && gy <= NYi - 2;
             const bool tile_col = col >= 1 && col <= TW - 2;
-            if (interior && tile_col) cols_upd |= pat;
+            if (interior) cols_upd |= pat;
             if (interior && col >= h && col < TW - h) cols_cnt |= pat;
             if (tile_col) cols_bc |= pat;
         }
@@ -328,16 +454,42 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
 
     mbar_wait(bar, 0);
 
-    // own pressures -> registers, for the whole pass
+    // own pressures -> registers (for the whole pass), then re-lay the warp's half rows of p
+    // and rhs in place: [32 first cells | 32 second cells] (see the header comment).  A warp
+    // only touches its own 64-column half rows here, so __syncwarp() orders reads and writes.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Thr th;
+    th.r_begin = r_begin;
+    th.bx = r_begin * TW + ((tc >> 5) << 6) + lane;
+    th.offL = lane > 0 ? 31 : -1;
+    th.offR = lane < 31 ? 1 : 33;
     double2 P[RPT];
 #pragma unroll
     for (int i = 0; i < RPT; i++) P[i] = lds2(sp, base + i * TW);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < RPT; i++) {
+        sp[th.bx + i * TW] = P[i].x;
+        sp[th.bx + i * TW + 32] = P[i].y;
+    }
+#pragma unroll
+    for (int g0 = 0; g0 < RPT; g0 += 4) {
+        double2 rr[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) rr[j] = lds2(sr, base + (g0 + j) * TW);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            sr[th.bx + (g0 + j) * TW] = rr[j].x;
+            sr[th.bx + (g0 + j) * TW + 32] = rr[j].y;
+        }
+    }
+    __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double acc_prev = 0.0, acc_cur = 0.0;
 
     if (norm_only) {
-        explicit_norm(P, sp, sr, base, r_begin, m.cnt, k, acc_cur);
+        explicit_norm<PAR>(P, sp, sr, th, m.cnt, m.upd, false, k, acc_cur);
         const double v = warp_sum(acc_cur);
         if (lane == 0) sred[warp] = v;
     }
@@ -351,9 +503,9 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
                         if (m.bc & (1u << (2 * i + e))) {
-                            const int idx = base + i * TW + e;
-                            const double v = bc_value(sp, idx, sf[idx]);
-                            sp[idx] = v;
+                            const int r = r_begin + i, col = col0 + e;
+                            const double v = bc_value(sp, r, col, sf[r * TW + col]);
+                            sp[th.bx + i * TW + e * 32] = v;
                             if (e) P[i].y = v; else P[i].x = v;
                         }
                     }
@@ -361,22 +513,21 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
             }
             __syncthreads();
         }
-        half_sweep<PAR, 0>(P, sp, sr, base, r_begin, m, it > 0 ? m_lag_all : 0u, k, acc_prev,
-                           acc_cur);
+        half_sweep<PAR, 0>(P, sp, sr, th, m, it > 0 ? m_lag_all : 0u, k, acc_prev, acc_cur);
         if (it > 0) {  // sweep it-1 is now complete in acc_prev
             const double v = warp_sum(acc_prev);
             if (lane == 0) sred[(it - 1) * NWARP + warp] = v;
         }
         __syncthreads();
         acc_prev = 0.0;
-        half_sweep<PAR, 1>(P, sp, sr, base, r_begin, m, 0u, k, acc_prev, acc_cur);
+        half_sweep<PAR, 1>(P, sp, sr, th, m, 0u, k, acc_prev, acc_cur);
         __syncthreads();
         // explicit residuals of this sweep: the rare cells every sweep, all red cells after
         // the last sweep of the pass
         const bool last = it == T - 1;
         if (has_exp || last) {
-            explicit_norm(P, sp, sr, base, r_begin, last ? (m.exp_ | (m.cnt & m_red)) : m.exp_, k,
-                          acc_cur);
+            explicit_norm<PAR>(P, sp, sr, th, last ? (m.exp_ | (m.cnt & m_red)) : m.exp_, m.upd,
+                               last, k, acc_cur);
             // before the next BC / red half-sweep overwrites cells these residuals read
             if (!last) __syncthreads();
         }

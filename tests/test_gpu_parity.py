@@ -320,31 +320,30 @@ def test_red_black_early_exit_inside_block(T):
 @pytest.mark.parametrize("eps", [1e-3, 1e-6])
 def test_red_black_vs_reference_order_converged(eps):
     """Performance mode against the REFERENCE ordering (SURVEY.md 8a A6 protocol): compare
-    on converged ticks, pressure up to its free constant.  Both orderings are started from
-    the same converged state (250 reference-order ticks of the channel; before that SOR hits
-    its cap every tick and the two orderings legitimately drift apart), run 10 more ticks and
-    must agree to a small multiple of the SOR epsilon -- each stops at a residual norm < eps.
-    Measured on the B200: 1.3 eps on u at eps = 1e-3; the tolerance is 3 eps."""
-    shape = (34, 18)
-    g = presets.simple_inflow(shape)
-    warm = Simulation.try_from(unfinalized(shape[0], shape[1], g["kind"], g["bu"], g["bv"]))
-    warm.run_ticks(250)
-    assert warm.run_simulation_tick()[0] < 100  # converged regime reached
-    unf = unfinalized(shape[0], shape[1], g["kind"], g["bu"], g["bv"], p=warm.grid.pressure,
-                      u=warm.grid.u, v=warm.grid.v, sor_absolute_epsilon=eps,
-                      max_iterations=5000, initial_norm_squared=0.0)
+    on converged ticks, pressure up to its free constant; tolerance 3 x the SOR epsilon.
+
+    The comparison needs a solvable pressure problem: in the inflow/outflow channel presets
+    the discrete Neumann problem is slightly inconsistent, the residual norm has a floor
+    (measured on the B200: ~1e-7 for the lexicographic order, ~4e-6 for red-black at tick
+    250 of the 34x18 channel) and "SOR to eps" is then decided by the cap, not by eps.  A
+    closed cavity with a moving lid has no net flux, both orderings converge every tick."""
+    shape = (34, 34)
+    g = presets.cavity(shape, lid_u=1.0)
+    unf = unfinalized(shape[0], shape[1], g["kind"], g["bu"], g["bv"], delx=1 / 32, dely=1 / 32,
+                      delt=2e-3, reynolds=100.0, sor_absolute_epsilon=eps, max_iterations=5000)
     rb = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK, temporal_block=2)
     lex = Simulation.try_from(unf, sor_mode=SOR_REFERENCE_ORDER)
-    for t in range(10):
+    for t in range(60):
         it_rb, n_rb = rb.run_simulation_tick()
         it_lex, n_lex = lex.run_simulation_tick()
-        assert it_rb < 5000 and it_lex < 5000 and n_rb < eps * eps and n_lex < eps * eps
+        assert it_rb < 5000 and it_lex < 5000, (t, it_rb, it_lex, n_rb, n_lex)
     fluid = g["kind"] == 0
     du = np.abs(rb.grid.u - lex.grid.u)[fluid].max()
     dv = np.abs(rb.grid.v - lex.grid.v)[fluid].max()
     prb, plex = rb.grid.pressure, lex.grid.pressure
     dp = np.abs((prb - prb[fluid].mean()) - (plex - plex[fluid].mean()))[fluid].max()
     tol = 3.0 * eps
+    assert np.abs(lex.grid.u)[fluid].max() > 0.05  # the lid has set the fluid in motion
     assert du <= tol and dv <= tol and dp <= tol, (du, dv, dp)
 
 
