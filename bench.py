@@ -24,6 +24,7 @@ like the Rust original) on a bounded sample of the same workload.
 """
 import argparse
 import ctypes as C
+import datetime
 import json
 import os
 import statistics
@@ -44,7 +45,10 @@ SOR_BYTES_PER_CELL_SWEEP = 25.0   # read p, rhs, flag; write p
 TICK_FIXED_BYTES_PER_CELL = 81.0  # F/G+RHS 40 + velocity update/ranges 41
 # dram__bytes_read.sum + dram__bytes_write.sum per sor_rb_kernel launch, from the committed
 # `ncu --set full` capture (profiles/); None until a capture for this configuration exists
-NCU_TRAFFIC_BYTES = {}
+NCU_TRAFFIC_BYTES = {
+    # profiles/r1_sor_rb_T2_8192_ncu_full.txt (algorithmic: 25 B x 8192^2 = 1 677 721 600)
+    "rb-T2-8192x8192": 1650447464,
+}
 
 
 def workload(name, n_gpus, size=None):
@@ -81,8 +85,11 @@ def workload(name, n_gpus, size=None):
 
 # ---- clocks ---------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line).
+
+    nvidia-smi needs ~0.5 s before its first sample, so the sampler is started ahead of the
+    warm-up; only the samples whose timestamp falls inside [begin(), end()] are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -90,15 +97,22 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.gpu_index)],
+                 "-lms", "50", "-i", str(self.gpu_index)],
                 stdout=self.tmp, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+
+    def begin(self):
+        self.t0 = datetime.datetime.now()
+
+    def end(self):
+        self.t1 = datetime.datetime.now()
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -112,12 +126,16 @@ class ClockSampler:
         self.tmp.flush()
         rows = [r.split(",") for r in Path(self.tmp.name).read_text().splitlines() if r.strip()]
         os.unlink(self.tmp.name)
-        sm, smax, reasons = [], [], set()
+        sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
             try:
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f")
+                if self.t0 and self.t1 and not (self.t0 <= ts <= self.t1):
+                    continue
                 sm.append(float(r[1]))
                 smax.append(float(r[2]))
+                power.append(float(r[3]))
             except (ValueError, IndexError):
                 continue
             for name, val in zip(names, r[5:9]):
@@ -125,7 +143,7 @@ class ClockSampler:
                     reasons.add(name)
         if sm:
             out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), samples=len(sm),
-                       reasons=sorted(reasons))
+                       power_w_max=max(power), reasons=sorted(reasons))
         return out
 
 
@@ -238,15 +256,16 @@ def run_ours(args):
         return float(t[0])
 
     # -- warm-up --------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     sweeps = []
     for _ in range(args.warmup):
         it, _ = sim.run_simulation_tick()
     # -- timed region: device-resident ticks -----------------------------------------------
-    sampler = ClockSampler(local_rank)
     launches0 = sim.kernel_launches
     sim.profile_enable(True)
     barrier()
-    sampler.start()
+    sampler.begin()
     sim.timer_begin()                         # CUDA event on the stream the kernels run on
     sor_ms = 0.0
     for _ in range(args.steps):
@@ -254,6 +273,7 @@ def run_ours(args):
         sweeps.append(it)
         sor_ms += sim.last_sor_ms
     dt = sim.timer_end() * 1e-3               # event + synchronize
+    sampler.end()
     barrier()
     clocks = sampler.stop()
     pass_ms = sim.profile_read()
@@ -358,7 +378,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5")
