@@ -233,14 +233,13 @@ def run_ours(args):
     nx, ny = wl["size"]
     mode = SOR_RED_BLACK if args.mode == "rb" else SOR_REFERENCE_ORDER
     ext = dict(sor_mode=mode, temporal_block=args.tblock, device=local_rank)
-    if world > 1:
-        from stroemung_b200 import multi
-        multi.init_comm(dist, rank, world, local_rank)
-        xb, xe = multi.slab_range(nx, rank, world)
-        ext.update(x_begin=xb, x_end=xe, rank=rank, world=world)
-    sim = Simulation.from_preset(wl["preset"], wl["size"], wl["cell_size"], wl["delt"],
-                                 wl["gamma"], wl["reynolds"], wl["eps"], wl["max_iterations"],
-                                 wl["omega"], preset_args=wl["preset_args"], **ext)
+    from stroemung_b200 import multi
+    # N > 1: one row slab per rank, connected GPU-to-GPU (CUDA IPC over NVLink); the host
+    # group only carries the connection blobs (stroemung_b200/multi.py)
+    group = multi.TorchGroup(dist) if world > 1 else multi.ThreadGroup(1).view(0)
+    sim = multi.from_preset(group, wl["preset"], wl["size"], wl["cell_size"], wl["delt"],
+                            wl["gamma"], wl["reynolds"], wl["eps"], wl["max_iterations"],
+                            wl["omega"], preset_args=wl["preset_args"], **ext)
     L = _capi.lib()
 
     def barrier():
@@ -302,6 +301,8 @@ def run_ours(args):
     for _ in range(e2e_steps):
         for hbuf, fld in zip(host, fields):
             sim._check(L.sb_upload(sim._h, fld, hbuf))      # H2D from pinned host memory
+        if world > 1:
+            sim.slab_sync_halos()                           # uploaded rows -> neighbours' halos
         sim.run_simulation_tick()
         for hbuf, fld in zip(host, fields):
             sim._check(L.sb_download(sim._h, fld, hbuf))    # D2H of the step's result
@@ -331,7 +332,10 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "25 B per cell-sweep x cells x sweeps per launch; CUDA events around "
                         "every launch of the timed region"}
+    barrier()
+    sim.close()
     if rank != 0:
+        dist.destroy_process_group()
         return 0
 
     # -- CPU baseline beside it (N = 1 only): bounded sample of the same workload -----------

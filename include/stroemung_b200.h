@@ -191,12 +191,27 @@ sb_status sb_create_preset(const sb_params *params, int32_t preset, const double
 sb_status sb_error_cell(const sb_sim *sim, uint64_t xy[2], uint8_t *kind);
 const char *sb_last_error_string(void);
 
-/* ---- multi-GPU (one handle per process per GPU, row slabs along x) -------------- */
-/* 128-byte opaque id created on rank 0 and distributed by the host (any channel);
- * then every rank calls sb_comm_init before sb_create with world > 1. */
-sb_status sb_comm_unique_id(uint8_t id[128]);
-sb_status sb_comm_init(const uint8_t id[128], int32_t rank, int32_t world, int32_t device);
-sb_status sb_comm_finalize(void);
+/* ---- multi-GPU: row slabs along x, one handle per GPU (one process per GPU) ---------
+ * The reference is single-process; this is the build's extension for grids beyond one
+ * GPU.  Protocol, every rank:
+ *   1. sb_create / sb_create_preset with world > 1 and this rank's [x_begin, x_end)
+ *      (>= 10 rows).  Host arrays cover the owned rows only; the velocity table must hold
+ *      every Inflow / MovingWall cell of the owned rows AND of 10 rows beyond either end.
+ *      The handle is not usable yet.
+ *   2. sb_slab_export -> a blob; the host all-gathers the blobs of all ranks (any channel).
+ *   3. sb_slab_connect(all blobs, rank order): maps the neighbours' halo rows and every
+ *      rank's mailbox (CUDA IPC over NVLink; handles of one process use peer access) and
+ *      finishes construction collectively (classification, ranges, F/G, RHS, initial norm).
+ * After that sb_tick & co. are collective calls: every rank makes the same calls in the
+ * same order.  p halos move inside the red-black pass (P2P stores), u/v halos after the
+ * velocity update, norms / ranges / counts through an all-gather in rank order, so all
+ * ranks return bit-identical scalars.  A peer that never shows up ends in SB_CUDA_ERROR
+ * after ~20 s, not in a hang.  Red-black mode only; sb_edit_cells is single-GPU. */
+#define SB_SLAB_BLOB_BYTES 1024
+sb_status sb_slab_export(sb_sim *sim, uint8_t blob[SB_SLAB_BLOB_BYTES]);
+sb_status sb_slab_connect(sb_sim *sim, const uint8_t *blobs, size_t n_blobs);
+/* after sb_upload of p / u / v on any rank (collective): refresh all halo rows */
+sb_status sb_slab_sync_halos(sb_sim *sim);
 
 /* ---- cell-level operators (src/math.rs, src/simulation.rs:349-392) --------------
  * Evaluated ON THE DEVICE with the same __device__ functions the kernels use, so

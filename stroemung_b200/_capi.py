@@ -16,6 +16,8 @@ LIB_PATH = Path(os.environ.get("SB_LIB", _DIR / "libstroemung_b200.so"))
  SB_INVALID_ARGUMENT) = range(5)
 KIND_FLUID, KIND_NOSLIP, KIND_OUTFLOW, KIND_INFLOW, KIND_MOVING_WALL = range(5)
 SOR_REFERENCE_ORDER, SOR_RED_BLACK = 0, 1
+SLAB_BLOB_BYTES = 1024
+SLAB_HALO = 10
 (FIELD_P, FIELD_U, FIELD_V, FIELD_F, FIELD_G, FIELD_RHS, FIELD_KIND, FIELD_EDGE) = range(8)
 EDGE_NAMES = ["None", "North", "NorthEast", "East", "SouthEast", "South", "SouthWest", "West",
               "NorthWest"]
@@ -65,7 +67,7 @@ SYMBOLS = [
     "sb_upload", "sb_host_alloc", "sb_host_free", "sb_get_state", "sb_set_params",
     "sb_set_boundary_velocities", "sb_rebuild_boundary_list", "sb_boundary_list",
     "sb_edit_cells", "sb_create_preset", "sb_error_cell", "sb_last_error_string",
-    "sb_comm_unique_id", "sb_comm_init", "sb_comm_finalize", "sb_du2dx", "sb_duvdx", "sb_duvdy",
+    "sb_slab_export", "sb_slab_connect", "sb_slab_sync_halos", "sb_du2dx", "sb_duvdx", "sb_duvdy",
     "sb_dv2dy", "sb_laplacian", "sb_residual", "sb_calculate_f", "sb_calculate_g",
     "sb_profile_enable", "sb_profile_read", "sb_timer_begin", "sb_timer_end", "sb_kernel_launches", "sb_last_sor_ms", "sb_stream",
     "sb_version",
@@ -110,9 +112,9 @@ def lib():
         "sb_edit_cells": ([vp, C.c_uint64, C.c_uint64, C.c_uint8, d, d, i32p], C.c_int),
         "sb_error_cell": ([vp, u64p, u8p], C.c_int),
         "sb_last_error_string": ([], C.c_char_p),
-        "sb_comm_unique_id": ([u8p], C.c_int),
-        "sb_comm_init": ([u8p, C.c_int32, C.c_int32, C.c_int32], C.c_int),
-        "sb_comm_finalize": ([], C.c_int),
+        "sb_slab_export": ([vp, u8p], C.c_int),
+        "sb_slab_connect": ([vp, u8p, C.c_size_t], C.c_int),
+        "sb_slab_sync_halos": ([vp], C.c_int),
         "sb_du2dx": ([dp, d, d, dp], C.c_int),
         "sb_duvdx": ([dp, dp, d, d, dp], C.c_int),
         "sb_duvdy": ([dp, dp, d, d, dp], C.c_int),

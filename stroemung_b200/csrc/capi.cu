@@ -59,6 +59,8 @@ static void destroy(sb_sim *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    slab_release(s);
+    cudaFree(s->d_hist);
     cudaFree(s->p[0]); cudaFree(s->p[1]); cudaFree(s->u); cudaFree(s->v); cudaFree(s->f);
     cudaFree(s->gq); cudaFree(s->rhs); cudaFree(s->cflag);
     cudaFree(s->bl.lin); cudaFree(s->bl.ke); cudaFree(s->bl.bu); cudaFree(s->bl.bv);
@@ -110,7 +112,17 @@ static sb_status allocate(const sb_params *params, sb_sim **out) {
             delete s;
             return SB_INVALID_ARGUMENT;
         }
-        s->halo = rb_halo_rows(4);
+        if (params->world > SB_MAX_WORLD || params->rank < 0 || params->rank >= params->world) {
+            set_error("params: bad rank / world (at most 16 slabs)");
+            delete s;
+            return SB_INVALID_ARGUMENT;
+        }
+        if (xe - xb < SB_SLAB_HALO) {
+            set_error("params: a slab needs at least 10 owned rows (the halo depth)");
+            delete s;
+            return SB_INVALID_ARGUMENT;
+        }
+        s->halo = SB_SLAB_HALO;
     }
     g.nxl = (xe - xb) + 2 * s->halo;
     g.gx0 = xb - s->halo;
@@ -149,6 +161,10 @@ static sb_status allocate(const sb_params *params, sb_sim **out) {
     SB_TRY(cudaEventCreate(&s->ev_sor1));
     SB_TRY(cudaEventCreate(&s->ev_t0));
     SB_TRY(cudaEventCreate(&s->ev_t1));
+    if (params->world > 1 && slab_prepare(s) != SB_OK) {
+        destroy(s);
+        return SB_CUDA_ERROR;
+    }
     SB_TRY(cudaStreamSynchronize(s->stream));
 #undef SB_TRY
     s->time = params->time;
@@ -206,7 +222,7 @@ static sb_status norm_now(sb_sim *s, double *out) {
 
 // Simulation::try_from after the arrays are in place (src/simulation.rs:92-96 and
 // src/grid/mod.rs:148-150): classify, ranges, F/G, RHS, initial norm
-static sb_status finish_create(sb_sim *s) {
+sb_status finish_create(sb_sim *s) {
     sb_status st;
     if ((st = classify(s))) return st;
     if ((st = sync_ctl_idle(s))) return st;
@@ -240,7 +256,18 @@ static sb_status solve(sb_sim *s, uint32_t max_it, int test_exit, uint32_t *iter
     const bool rb = is_rb(s);
     const int T = rb ? s->prm.temporal_block : 1;
     double *d_hist = nullptr;
-    if (norm_hist_host && max_it) SB_CUDA(cudaMalloc(&d_hist, (size_t)max_it * sizeof(double)));
+    if (norm_hist_host && max_it) {
+        if (s->hist_cap < max_it) {
+            // grows only; stream-ordered so that no device-wide synchronisation happens while
+            // another slab of this process may be waiting for this one
+            if (s->d_hist) SB_CUDA(cudaFreeAsync(s->d_hist, s->stream));
+            s->d_hist = nullptr;
+            s->hist_cap = 0;
+            SB_CUDA(cudaMallocAsync(&s->d_hist, (size_t)max_it * sizeof(double), s->stream));
+            s->hist_cap = max_it;
+        }
+        d_hist = s->d_hist;
+    }
     SB_CUDA(cudaEventRecord(s->ev_sor0, s->stream));
     if (max_it == 0 || s->g.NX < 3 || s->g.NY < 3) {
         // no interior: the sweep and the norm are empty loops (0.0 / fluid_cells)
@@ -262,7 +289,6 @@ static sb_status solve(sb_sim *s, uint32_t max_it, int test_exit, uint32_t *iter
             if ((st = launch_pressure_range(s))) return st;
         *iters = it;
         *norm = n;
-        if (d_hist) cudaFree(d_hist);
         return SB_OK;
     }
     SorCtl *h = s->h_ctl;
@@ -306,9 +332,9 @@ static sb_status solve(sb_sim *s, uint32_t max_it, int test_exit, uint32_t *iter
     *iters = h->iters_done;
     *norm = h->last_norm;
     if (d_hist) {
-        SB_CUDA(cudaMemcpy(norm_hist_host, d_hist, (size_t)h->iters_done * sizeof(double),
-                           cudaMemcpyDeviceToHost));
-        cudaFree(d_hist);
+        SB_CUDA(cudaMemcpyAsync(norm_hist_host, d_hist, (size_t)h->iters_done * sizeof(double),
+                                cudaMemcpyDeviceToHost, s->stream));
+        SB_CUDA(cudaStreamSynchronize(s->stream));
     }
     int cap_hit = h->cap_hit;
     if ((st = sync_ctl_idle(s))) return st;
@@ -332,7 +358,7 @@ static sb_status tick(sb_sim *s, uint32_t *iters, double *norm) {
     s->last_norm_squared = *norm;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, s->ev_sor0, s->ev_sor1) == cudaSuccess) s->last_sor_ms = ms;
-    return SB_OK;
+    return slab_check_error(s);
 }
 
 }  // namespace sb
@@ -342,6 +368,10 @@ using namespace sb;
 #define SB_ENTER(s)                                   \
     if (!(s)) {                                       \
         set_error("null handle");                     \
+        return SB_INVALID_ARGUMENT;                   \
+    }                                                 \
+    if ((s)->slab && !(s)->connected) {               \
+        set_error("slab handle: call sb_slab_connect first"); \
         return SB_INVALID_ARGUMENT;                   \
     }                                                 \
     SB_CUDA(cudaSetDevice((s)->device))
@@ -376,7 +406,9 @@ sb_status sb_create(const sb_params *params, const double *p, const double *u, c
     if ((st = copy_rows_h2d(s, s->cflag, kind, 1))) return fail(st);
     if ((st = launch_mark_valid(s, nullptr, 0))) return fail(st);
     if (velocities && n_velocities) s->velocities.assign(velocities, velocities + n_velocities);
-    if ((st = finish_create(s))) return fail(st);
+    // a slab finishes construction collectively in sb_slab_connect
+    if (!s->slab && (st = finish_create(s))) return fail(st);
+    SB_CUDA(cudaStreamSynchronize(s->stream));
     *out = s;
     return SB_OK;
 }
@@ -419,7 +451,8 @@ sb_status sb_create_preset(const sb_params *params, int32_t preset, const double
         for (int64_t x = 1; x <= NX - 2; x++)
             s->velocities.push_back(sb_boundary_velocity{(uint64_t)x, 0, lid_u, 0.0});
     }
-    if ((st = finish_create(s))) return fail(st);
+    if (!s->slab && (st = finish_create(s))) return fail(st);
+    SB_CUDA(cudaStreamSynchronize(s->stream));
     *out = s;
     return SB_OK;
 }
@@ -578,12 +611,12 @@ sb_status sb_upload(sb_sim *sim, sb_field field, const void *src) {
         // new kinds, old edge classes: like the reference, the boundary list is stale until
         // sb_rebuild_boundary_list (src/lib.rs:60-70)
         uint8_t *tmp = nullptr;
-        SB_CUDA(cudaMalloc(&tmp, sim->flag_bytes));
+        SB_CUDA(cudaMallocAsync(&tmp, sim->flag_bytes, sim->stream));
         SB_CUDA(cudaMemsetAsync(tmp, 0, sim->flag_bytes, sim->stream));
-        if ((st = copy_rows_h2d(sim, tmp, src, 1))) { cudaFree(tmp); return st; }
+        if ((st = copy_rows_h2d(sim, tmp, src, 1))) { cudaFreeAsync(tmp, sim->stream); return st; }
         st = launch_mark_valid(sim, tmp, 1);
+        cudaFreeAsync(tmp, sim->stream);
         cudaStreamSynchronize(sim->stream);
-        cudaFree(tmp);
         return st;
     }
     if (field == SB_FIELD_EDGE) {
@@ -656,7 +689,9 @@ sb_status sb_set_boundary_velocities(sb_sim *sim, const sb_boundary_velocity *v,
 
 sb_status sb_rebuild_boundary_list(sb_sim *sim) {
     SB_ENTER(sim);
-    sb_status st = classify(sim);
+    sb_status st;
+    if (sim->slab && (st = slab_sync_halos(sim, 1))) return st;  // kinds of the halo rows
+    st = classify(sim);
     if (st == SB_BOUNDARY_TOO_THIN) {
         g_err_xy[0] = sim->err_xy[0];
         g_err_xy[1] = sim->err_xy[1];
@@ -691,6 +726,10 @@ sb_status sb_edit_cells(sb_sim *sim, uint64_t x, uint64_t y, uint8_t kind, doubl
                         int32_t *applied) {
     SB_ENTER(sim);
     if (kind > SB_KIND_MOVING_WALL) return SB_INVALID_ARGUMENT;
+    if (sim->slab) {
+        set_error("sb_edit_cells: interactive edits are single-GPU (the GUI path)");
+        return SB_INVALID_ARGUMENT;
+    }
     sb_status st;
     double *d_backup = sim->d_scalars + 8;  // 20 doubles + 1 flag word
     int32_t *d_mod = reinterpret_cast<int32_t *>(sim->d_scalars + 32);
@@ -739,20 +778,6 @@ sb_status sb_error_cell(const sb_sim *sim, uint64_t xy[2], uint8_t *kind) {
 }
 
 const char *sb_last_error_string(void) { return g_error.c_str(); }
-
-sb_status sb_comm_unique_id(uint8_t id[128]) {
-    (void)id;
-    set_error("multi-GPU slabs: not built into this library yet");
-    return SB_INVALID_ARGUMENT;
-}
-
-sb_status sb_comm_init(const uint8_t id[128], int32_t rank, int32_t world, int32_t device) {
-    (void)id; (void)rank; (void)world; (void)device;
-    set_error("multi-GPU slabs: not built into this library yet");
-    return SB_INVALID_ARGUMENT;
-}
-
-sb_status sb_comm_finalize(void) { return SB_OK; }
 
 static sb_status cellop(int op, const double *u, const double *v, double s0, double s1, double s2,
                         double s3, double s4, double *out) {

@@ -206,29 +206,34 @@ __global__ void velocity_kernel(const sb_boundary_velocity *__restrict__ tab, si
     }
 }
 
+// All transient device memory is stream-ordered (cudaMallocAsync / cudaFreeAsync): a plain
+// cudaFree synchronises the whole device, which would stall on -- and with two slabs of one
+// process on one GPU deadlock against -- a peer's waiting all-gather kernel.
 template <typename T>
-sb_status ensure(T *&ptr, size_t &cap, size_t need) {
+sb_status ensure(cudaStream_t st, T *&ptr, size_t &cap, size_t need) {
     if (need <= cap) return SB_OK;
-    if (ptr) cudaFree(ptr);
+    if (ptr) SB_CUDA(cudaFreeAsync(ptr, st));
     ptr = nullptr;
+    cap = 0;
     size_t ncap = need + need / 4 + 64;
-    SB_CUDA(cudaMalloc(&ptr, ncap * sizeof(T)));
+    SB_CUDA(cudaMallocAsync(&ptr, ncap * sizeof(T), st));
     cap = ncap;
     return SB_OK;
 }
 
-void free_list(BList &b) {
-    cudaFree(b.lin); cudaFree(b.ke); cudaFree(b.bu); cudaFree(b.bv); cudaFree(b.ru);
-    cudaFree(b.rv); cudaFree(b.nu); cudaFree(b.nv); cudaFree(b.wu); cudaFree(b.wv);
+void free_list(cudaStream_t st, BList &b) {
+    void *ptrs[] = {b.lin, b.ke, b.bu, b.bv, b.ru, b.rv, b.nu, b.nv, b.wu, b.wv};
+    for (void *p : ptrs)
+        if (p) cudaFreeAsync(p, st);
     b = BList();
 }
 
-sb_status alloc_list(BList &b, uint64_t n) {
+sb_status alloc_list(cudaStream_t st, BList &b, uint64_t n) {
     uint64_t cap = n + 16;
-    SB_CUDA(cudaMalloc(&b.lin, cap * sizeof(int64_t)));
-    SB_CUDA(cudaMalloc(&b.ke, cap));
+    SB_CUDA(cudaMallocAsync(&b.lin, cap * sizeof(int64_t), st));
+    SB_CUDA(cudaMallocAsync(&b.ke, cap, st));
     double **arrs[] = {&b.bu, &b.bv, &b.ru, &b.rv, &b.nu, &b.nv, &b.wu, &b.wv};
-    for (double **a : arrs) SB_CUDA(cudaMalloc(a, cap * sizeof(double)));
+    for (double **a : arrs) SB_CUDA(cudaMallocAsync(a, cap * sizeof(double), st));
     b.n = n;
     b.cap = cap;
     return SB_OK;
@@ -251,18 +256,47 @@ sb_status classify(sb_sim *s) {
     unsigned long long res[2];
     SB_CUDA(cudaMemcpyAsync(res, s->d_err, sizeof(res), cudaMemcpyDeviceToHost, s->stream));
     SB_CUDA(cudaStreamSynchronize(s->stream));
+    uint8_t err_kind = 0;
+    if (res[0] != ~0ull) {
+        uint8_t fl = 0;
+        int64_t ex = (int64_t)(res[0] / (unsigned long long)g.NY);
+        int64_t ey = (int64_t)(res[0] % (unsigned long long)g.NY);
+        SB_CUDA(cudaMemcpyAsync(&fl, s->cflag + (ex - g.gx0) * g.pitch + ey, 1,
+                                cudaMemcpyDeviceToHost, s->stream));
+        SB_CUDA(cudaStreamSynchronize(s->stream));
+        err_kind = (uint8_t)cf_kind(fl);
+    }
+    if (s->slab) {
+        // first offender in x-major order over ALL slabs (min of index * 8 + kind; indices
+        // stay far below 2^50, exact in a double) and the global fluid count
+        s->h_scalars[0] = res[0] != ~0ull ? (double)res[0] * 8.0 + (double)err_kind : 1e300;
+        s->h_scalars[1] = (double)res[1];
+        SB_CUDA(cudaMemcpyAsync(s->d_scalars, s->h_scalars, 2 * sizeof(double),
+                                cudaMemcpyHostToDevice, s->stream));
+        sb_status st2 = slab_allreduce(s, s->d_scalars, 2, XR_MIN | (XR_SUM << 2));
+        if (st2) return st2;
+        SB_CUDA(cudaMemcpyAsync(s->h_scalars, s->d_scalars, 2 * sizeof(double),
+                                cudaMemcpyDeviceToHost, s->stream));
+        SB_CUDA(cudaStreamSynchronize(s->stream));
+        if ((st2 = slab_check_error(s))) return st2;
+        if (s->h_scalars[0] < 1e299) {
+            unsigned long long idx = (unsigned long long)(s->h_scalars[0] / 8.0);
+            err_kind = (uint8_t)(s->h_scalars[0] - (double)idx * 8.0);
+            res[0] = idx;
+        } else {
+            res[0] = ~0ull;
+        }
+        res[1] = (unsigned long long)s->h_scalars[1];
+    }
     if (res[0] != ~0ull) {
         s->err_xy[0] = res[0] / (unsigned long long)g.NY;
         s->err_xy[1] = res[0] % (unsigned long long)g.NY;
-        uint8_t fl = 0;
-        int64_t c = ((int64_t)s->err_xy[0] - g.gx0) * g.pitch + (int64_t)s->err_xy[1];
-        SB_CUDA(cudaMemcpy(&fl, s->cflag + c, 1, cudaMemcpyDeviceToHost));
-        s->err_kind = (uint8_t)cf_kind(fl);
+        s->err_kind = err_kind;
         set_error("BoundaryTooThinError: cell has fluid on opposing sides");
         return SB_BOUNDARY_TOO_THIN;
     }
     int64_t nchunks = (total + CL_CHUNK - 1) / CL_CHUNK;
-    sb_status st = ensure(s->d_scan, s->scan_cap, (size_t)nchunks + 1);
+    sb_status st = ensure(s->stream, s->d_scan, s->scan_cap, (size_t)nchunks + 1);
     if (st) return st;
     count_kernel<<<(int)nchunks, CL_THREADS, 0, s->stream>>>(s->cflag, g, s->d_scan);
     scan_kernel<<<1, 1024, 0, s->stream>>>(s->d_scan, nchunks);
@@ -271,8 +305,8 @@ sb_status classify(sb_sim *s) {
     SB_CUDA(cudaMemcpyAsync(&nlist, s->d_scan + nchunks, sizeof(int64_t), cudaMemcpyDeviceToHost,
                             s->stream));
     SB_CUDA(cudaStreamSynchronize(s->stream));
-    free_list(s->bl);
-    st = alloc_list(s->bl, (uint64_t)nlist);
+    free_list(s->stream, s->bl);
+    st = alloc_list(s->stream, s->bl, (uint64_t)nlist);
     if (st) return st;
     fill_kernel<<<(int)nchunks, CL_THREADS, 0, s->stream>>>(s->cflag, g, s->d_scan, s->bl.lin,
                                                             s->bl.ke, s->bl.bu, s->bl.bv);
@@ -286,15 +320,28 @@ sb_status apply_velocity_table(sb_sim *s) {
     size_t n = s->velocities.size();
     if (n == 0 || s->bl.n == 0) return SB_OK;
     sb_boundary_velocity *d_tab = nullptr;
-    SB_CUDA(cudaMalloc(&d_tab, n * sizeof(sb_boundary_velocity)));
+    SB_CUDA(cudaMallocAsync(&d_tab, n * sizeof(sb_boundary_velocity), s->stream));
     SB_CUDA(cudaMemcpyAsync(d_tab, s->velocities.data(), n * sizeof(sb_boundary_velocity),
                             cudaMemcpyHostToDevice, s->stream));
     velocity_kernel<<<(int)((n + 255) / 256), 256, 0, s->stream>>>(
         d_tab, n, s->g, s->bl.lin, s->bl.ke, s->bl.n, s->bl.bu, s->bl.bv);
     s->launches++;
+    SB_CUDA(cudaFreeAsync(d_tab, s->stream));
     SB_CUDA(cudaStreamSynchronize(s->stream));
-    SB_CUDA(cudaFree(d_tab));
     return SB_OK;
+}
+
+// force-load this file's kernels (CUDA loads lazily by default, and a first launch that has
+// to load code synchronises the context -- fatal while a peer slab of the same process spins
+// in an all-gather on the same GPU)
+void preload_classify() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, edge_kernel);
+    cudaFuncGetAttributes(&a, count_kernel);
+    cudaFuncGetAttributes(&a, scan_kernel);
+    cudaFuncGetAttributes(&a, fill_kernel);
+    cudaFuncGetAttributes(&a, velocity_kernel);
+    cudaGetLastError();
 }
 
 }  // namespace sb

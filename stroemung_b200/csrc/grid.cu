@@ -188,4 +188,17 @@ sb_status launch_edit_block(sb_sim *s, int64_t gx, int64_t gy, uint8_t kind, dou
     return SB_OK;
 }
 
+// force-load this file's kernels (CUDA loads lazily by default, and a first launch that has
+// to load code synchronises the context -- fatal while a peer slab of the same process spins
+// in an all-gather on the same GPU)
+void preload_grid() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, mark_valid_kernel);
+    cudaFuncGetAttributes(&a, clear_edges_kernel);
+    cudaFuncGetAttributes(&a, list_edges_kernel);
+    cudaFuncGetAttributes(&a, preset_kernel);
+    cudaFuncGetAttributes(&a, edit_block_kernel);
+    cudaGetLastError();
+}
+
 }  // namespace sb

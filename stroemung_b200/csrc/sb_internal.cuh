@@ -65,6 +65,34 @@ struct SorCtl {        // device-resident control block of one SOR solve
     double norms[8];   // norms of the last pass (diagnostics / sb_sor_sweeps)
 };
 
+// ---- row-slab decomposition (slab.cu) ---------------------------------------------------
+constexpr int SB_MAX_WORLD = 16;
+constexpr int SB_SLAB_HALO = 10;   // = rb_halo_rows(4): halo rows on each side of a slab
+
+// One mailbox slot: a rank's contribution to one all-gather round (slab.cu)
+struct MailSlot {
+    double vals[8];
+    unsigned long long seq;
+    unsigned long long pad[7];
+};
+static_assert(sizeof(MailSlot) == 128, "one slot per 128-byte line");
+
+// What a kernel needs to talk to the other slabs; passed by value.  All pointers are valid
+// in THIS process (CUDA IPC mappings or, for handles of the same process, the peers' own
+// allocations).  world <= 1: single GPU, nothing here is touched.
+struct SlabLink {
+    int32_t rank, world;
+    int32_t H;                       // halo rows
+    int32_t pad;
+    MailSlot *mbox[SB_MAX_WORLD];    // [2][SB_MAX_WORLD] slots of every rank (own included)
+    unsigned long long *seq;         // this rank's round counter (device memory)
+    int32_t *err;                    // set to 1 when a wait timed out (device memory)
+    // pressure buffers of the chain neighbours (nullptr at the ends of the chain) and the
+    // local row of THEIR array that receives my first / last H owned rows
+    double *lo_p[2], *hi_p[2];
+    int64_t lo_row0, hi_row0;
+};
+
 #define SB_CUDA(call)                                                               \
     do {                                                                            \
         cudaError_t _e = (call);                                                    \
@@ -128,6 +156,18 @@ struct sb_sim {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;  // pairs: begin, end
     size_t prof_used = 0;
+    // row-slab mode (prm.world > 1): links to the other slabs, see slab.cu
+    bool slab = false, connected = false;
+    sb::SlabLink link{};
+    sb::MailSlot *d_mbox = nullptr;
+    unsigned long long *d_xseq = nullptr;
+    int32_t *d_xerr = nullptr;
+    std::vector<void *> ipc_opened;           // bases returned by cudaIpcOpenMemHandle
+    // neighbours' u, v, cflag arrays (halo puts outside the SOR passes)
+    double *lo_u = nullptr, *lo_v = nullptr, *hi_u = nullptr, *hi_v = nullptr;
+    uint8_t *lo_flag = nullptr, *hi_flag = nullptr;
+    double *d_hist = nullptr;                 // norm history of sb_sor_sweeps (grows only)
+    size_t hist_cap = 0;
     // tensor maps for the red-black pass (built lazily per buffer)
     bool tmaps_ready = false;
     CUtensorMap tm_p[2], tm_rhs, tm_flag;
@@ -167,5 +207,23 @@ sb_status launch_mark_valid(sb_sim *s, const uint8_t *d_kind_rows, int keep_edge
 sb_status launch_preset(sb_sim *s, int preset, const double *args);
 sb_status launch_edit_block(sb_sim *s, int64_t gx, int64_t gy, uint8_t kind, double *backup,
                             int restore, int32_t *modified);
+// slab.cu -- cross-slab primitives (no-ops / identity for a single-GPU handle)
+enum { XR_SUM = 0, XR_MIN = 1, XR_MAX = 2 };
+// d_vals[0..n) (device, n <= 8) := reduction over all slabs, op of value i = (ops >> 2i) & 3;
+// every slab gets bit-identical results (fixed rank order).  n = 0: barrier only.
+sb_status slab_allreduce(sb_sim *s, double *d_vals, int n, unsigned ops);
+// my first / last H owned rows of a field -> the neighbours' halo rows (no barrier)
+sb_status slab_put_rows(sb_sim *s, const void *field, void *lo_field, void *hi_field,
+                        size_t esize);
+// p[cur], u, v (and optionally cflag) halos of all slabs made current: barrier, puts, barrier
+sb_status slab_sync_halos(sb_sim *s, int with_flags);
+sb_status slab_check_error(sb_sim *s);
+void preload_classify();
+void preload_grid();
+void preload_stages();
+void preload_sor_rb();
+sb_status slab_prepare(sb_sim *s);   // mailbox etc. of a world > 1 handle
+sb_status finish_create(sb_sim *s);  // capi.cu: try_from's work once the arrays are in place
+void slab_release(sb_sim *s);
 
 }  // namespace sb

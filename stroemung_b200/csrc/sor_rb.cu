@@ -71,6 +71,14 @@ struct RbConsts {
     double rdx2, rdy2, diag, mid, omw;
 };
 
+// row-slab mode: the neighbours' pressure buffers (nullptr at the chain ends / single GPU)
+// and the row of THEIR array that receives my first (lo) / last (hi) H owned rows
+struct RbPeers {
+    double *lo_p[2], *hi_p[2];
+    int64_t lo_row0, hi_row0;
+    int H;
+};
+
 // ---- mbarrier / TMA wrappers (inline PTX) -------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -336,7 +344,7 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
               const __grid_constant__ CUtensorMap tm_rhs, const uint8_t *__restrict__ cflag,
               Geom g, double *const *__restrict__ pbuf, const SorCtl *__restrict__ ctl,
               double *__restrict__ partial, int tiles_y, int ntiles, int h, RbConsts k,
-              int norm_only) {
+              int norm_only, RbPeers peers) {
     // norm_only: no sweeps, no write-back; partial[tile] = sum of squared residuals of the
     // current field (calculate_norm_squared on its own, src/simulation.rs:216-227)
     const int T = norm_only ? 0 : ctl->active_T;
@@ -352,7 +360,7 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
 
     const int BX = TXR - 2 * h, BY = TW - 2 * h;  // h is even: owned columns 16-byte aligned
     const int tile_i = blockIdx.x / tiles_y, tile_j = blockIdx.x - tile_i * tiles_y;
-    const int tx0 = tile_i * BX - h;   // local row of tile row 0 (even)
+    const int tx0 = (int)g.own0 + tile_i * BX - h;  // local row of tile row 0 (even)
     const int ty0 = tile_j * BY - h;   // column of tile column 0 (even)
 
     if (threadIdx.x == 0) {
@@ -390,7 +398,10 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
         const uint32_t rows_cnt =
             row_bits(max(max(int_lo, own_lo), h), min(min(int_hi, own_hi), TXR - h), r_begin);
         const uint32_t rows_bc = row_bits(max(in_lo, 1), min(in_hi, TXR - 1), r_begin);
-        const uint32_t rows_st = row_bits(max(in_lo, h), min(in_hi, TXR - h), r_begin);
+        // stored: the exact inner rows this slab owns (its halo rows belong to the neighbours,
+        // who write them from their own epilogue below)
+        const uint32_t rows_st =
+            row_bits(max(max(in_lo, own_lo), h), min(min(in_hi, own_hi), TXR - h), r_begin);
         // column properties of the two cells -> 0x555555 / 0xAAAAAA patterns
         uint32_t cols_upd = 0, cols_cnt = 0, cols_bc = 0;
 #pragma unroll
@@ -551,6 +562,30 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
                 else dst[0] = P[i].x;
             }
         }
+        // halo exchange fused into the pass: rows within H of a slab edge also go straight
+        // into the neighbour's halo rows of ITS target buffer (P2P stores over NVLink); the
+        // all-gather of the finalize kernel that follows is the release/acquire point
+        if (peers.lo_p[0] || peers.hi_p[0]) {
+            const int lx0 = tx0 + r_begin;
+            const int own0 = (int)g.own0, own1 = (int)g.own1;
+#pragma unroll
+            for (int i = 0; i < RPT; i++) {
+                if (!(m_store & (1u << (2 * i)))) continue;
+                const int lx = lx0 + i;
+                if (peers.lo_p[0] && lx < own0 + peers.H) {
+                    double *dst = peers.lo_p[src ^ 1] +
+                                  (peers.lo_row0 + (lx - own0)) * g.pitch + gy0;
+                    if (pair) *reinterpret_cast<double2 *>(dst) = P[i];
+                    else dst[0] = P[i].x;
+                }
+                if (peers.hi_p[0] && lx >= own1 - peers.H) {
+                    double *dst = peers.hi_p[src ^ 1] +
+                                  (peers.hi_row0 + (lx - (own1 - peers.H))) * g.pitch + gy0;
+                    if (pair) *reinterpret_cast<double2 *>(dst) = P[i];
+                    else dst[0] = P[i].x;
+                }
+            }
+        }
     }
 
     // per-sweep residual sums of the tile (fixed order => deterministic)
@@ -624,15 +659,21 @@ sb_status launch_sor_rb_pass(sb_sim *s, int *ntiles_out, int norm_only) {
     int T = s->prm.temporal_block;
     int h = rb_halo_rows(T);
     int BX = TXR - 2 * h, BY = TW - 2 * h;
-    int tiles_x = (int)((g.nxl + BX - 1) / BX), tiles_y = (int)((g.NY + BY - 1) / BY);
+    int tiles_x = (int)((g.own1 - g.own0 + BX - 1) / BX), tiles_y = (int)((g.NY + BY - 1) / BY);
     int ntiles = tiles_x * tiles_y;
     size_t need = (size_t)ntiles * TMAX + 64;
-    if (need > s->partial_cap) {
-        if (s->d_partial) cudaFree(s->d_partial);
+    if (need > s->partial_cap) {  // stream-ordered: no device-wide synchronisation
+        if (s->d_partial) SB_CUDA(cudaFreeAsync(s->d_partial, s->stream));
         s->d_partial = nullptr;
-        SB_CUDA(cudaMalloc(&s->d_partial, need * sizeof(double)));
+        s->partial_cap = 0;
+        SB_CUDA(cudaMallocAsync(&s->d_partial, need * sizeof(double), s->stream));
         s->partial_cap = need;
     }
+    RbPeers peers;
+    peers.lo_p[0] = s->link.lo_p[0]; peers.lo_p[1] = s->link.lo_p[1];
+    peers.hi_p[0] = s->link.hi_p[0]; peers.hi_p[1] = s->link.hi_p[1];
+    peers.lo_row0 = s->link.lo_row0; peers.hi_row0 = s->link.hi_row0;
+    peers.H = s->link.H;
     RbConsts k;
     double dx2 = s->prm.delx * s->prm.delx, dy2 = s->prm.dely * s->prm.dely;
     k.rdx2 = 1.0 / dx2;
@@ -647,16 +688,26 @@ sb_status launch_sor_rb_pass(sb_sim *s, int *ntiles_out, int norm_only) {
     if (par)
         sor_rb_kernel<1><<<ntiles, NTHR, SMEM_BYTES, s->stream>>>(
             s->tm_p[0], s->tm_p[1], s->tm_rhs, s->cflag, g, pbuf_ptr(s), s->d_ctl, s->d_partial,
-            tiles_y, ntiles, h, k, norm_only);
+            tiles_y, ntiles, h, k, norm_only, peers);
     else
         sor_rb_kernel<0><<<ntiles, NTHR, SMEM_BYTES, s->stream>>>(
             s->tm_p[0], s->tm_p[1], s->tm_rhs, s->cflag, g, pbuf_ptr(s), s->d_ctl, s->d_partial,
-            tiles_y, ntiles, h, k, norm_only);
+            tiles_y, ntiles, h, k, norm_only, peers);
     if (!norm_only) prof_mark(s);
     s->launches++;
     SB_CUDA(cudaGetLastError());
     *ntiles_out = ntiles;
     return SB_OK;
+}
+
+// force-load this file's kernels (CUDA loads lazily by default, and a first launch that has
+// to load code synchronises the context -- fatal while a peer slab of the same process spins
+// in an all-gather on the same GPU)
+void preload_sor_rb() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, sor_rb_kernel<0>);
+    cudaFuncGetAttributes(&a, sor_rb_kernel<1>);
+    cudaGetLastError();
 }
 
 }  // namespace sb

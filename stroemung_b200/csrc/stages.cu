@@ -11,6 +11,7 @@
 // is contracted; see cellops.cuh for the operator restatements.
 #include "cellops.cuh"
 #include "sb_internal.cuh"
+#include "slab_dev.cuh"
 
 #include <float.h>
 
@@ -280,9 +281,12 @@ __global__ void norm_partial_kernel(Geom g, double *const *__restrict__ pbuf,
 // is repeated from the same source buffer with T = k (deterministic, so it then ends at k).
 __global__ void sor_finalize_kernel(SorCtl *__restrict__ ctl, const double *__restrict__ partial,
                                     int nparts, double fluid_cells, double initial_norm,
-                                    double eps2, int test_exit, double *__restrict__ norm_hist) {
+                                    double eps2, int test_exit, double *__restrict__ norm_hist,
+                                    SlabLink lk) {
     __shared__ double sh[1024 / 32];
+    __shared__ double level_sum[8];
     __shared__ double level_norm[8];
+    __shared__ double gathered[SB_MAX_WORLD * 8];
     int T = ctl->active_T;
     if (T == 0) return;
     for (int lvl = 0; lvl < T; lvl++) {
@@ -295,10 +299,29 @@ __global__ void sor_finalize_kernel(SorCtl *__restrict__ ctl, const double *__re
         if (threadIdx.x == 0) {
             double t = 0.0;
             for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += sh[k];
-            level_norm[lvl] = t / fluid_cells;
+            level_sum[lvl] = t;
         }
         __syncthreads();
     }
+    if (lk.world > 1) {
+        // row slabs: every rank sums the per-slab totals in rank order -> identical norms and
+        // identical exit decisions on all GPUs, no host in the loop (slab_dev.cuh)
+        if (!slab_allgather(lk, level_sum, T, gathered)) {
+            if (threadIdx.x == 0) {  // a peer went missing: end the solve, the host reports it
+                ctl->active_T = 0;
+                ctl->finished = 1;
+            }
+            return;
+        }
+        if ((int)threadIdx.x < T) {
+            double t = gathered[threadIdx.x];
+            for (int r = 1; r < lk.world; r++) t += gathered[r * 8 + threadIdx.x];
+            level_sum[threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+    if ((int)threadIdx.x < T) level_norm[threadIdx.x] = level_sum[threadIdx.x] / fluid_cells;
+    __syncthreads();
     if (threadIdx.x != 0) return;
     int exit_at = 0;
     for (int lvl = 0; lvl < T; lvl++) {
@@ -331,7 +354,7 @@ __global__ void sor_finalize_kernel(SorCtl *__restrict__ ctl, const double *__re
 
 // out[0] = (sum of partial[0..n)) / fluid_cells, same tree as the finalize kernel
 __global__ void sum_partials_kernel(const double *__restrict__ partial, int nparts,
-                                    double fluid_cells, double *__restrict__ out) {
+                                    double fluid_cells, double *__restrict__ out, int divide) {
     __shared__ double sh[1024 / 32];
     double acc = 0.0;
     for (int i = threadIdx.x; i < nparts; i += blockDim.x) acc += partial[i];
@@ -341,7 +364,7 @@ __global__ void sum_partials_kernel(const double *__restrict__ partial, int npar
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += sh[k];
-        out[0] = t / fluid_cells;
+        out[0] = divide ? t / fluid_cells : t;
     }
 }
 
@@ -504,9 +527,11 @@ dim3 row_grid(const Geom &g, int64_t rows, int64_t cols) {
 
 sb_status ensure_partial(sb_sim *s, size_t need) {
     if (need <= s->partial_cap) return SB_OK;
-    if (s->d_partial) cudaFree(s->d_partial);
+    // stream-ordered (no device-wide synchronisation, see solve() in capi.cu)
+    if (s->d_partial) SB_CUDA(cudaFreeAsync(s->d_partial, s->stream));
     s->d_partial = nullptr;
-    SB_CUDA(cudaMalloc(&s->d_partial, need * sizeof(double)));
+    s->partial_cap = 0;
+    SB_CUDA(cudaMallocAsync(&s->d_partial, need * sizeof(double), s->stream));
     s->partial_cap = need;
     return SB_OK;
 }
@@ -577,7 +602,7 @@ sb_status launch_sor_finalize(sb_sim *s, int nparts, double initial_norm, double
                               int test_exit, double *norm_hist) {
     sor_finalize_kernel<<<1, 1024, 0, s->stream>>>(s->d_ctl, s->d_partial, nparts,
                                                    s->fluid_cells, initial_norm, eps2,
-                                                   test_exit, norm_hist);
+                                                   test_exit, norm_hist, s->link);
     s->launches++;
     SB_CUDA(cudaGetLastError());
     return SB_OK;
@@ -585,18 +610,23 @@ sb_status launch_sor_finalize(sb_sim *s, int nparts, double initial_norm, double
 
 sb_status reduce_norm(sb_sim *s, int nparts, double *out) {
     sum_partials_kernel<<<1, 1024, 0, s->stream>>>(s->d_partial, nparts, s->fluid_cells,
-                                                   s->d_scalars);
+                                                   s->d_scalars, s->slab ? 0 : 1);
     s->launches++;
+    sb_status st = slab_allreduce(s, s->d_scalars, 1, XR_SUM);
+    if (st) return st;
     SB_CUDA(cudaMemcpyAsync(s->h_scalars, s->d_scalars, sizeof(double), cudaMemcpyDeviceToHost,
                             s->stream));
     SB_CUDA(cudaStreamSynchronize(s->stream));
-    *out = s->h_scalars[0];
+    *out = s->slab ? s->h_scalars[0] / s->fluid_cells : s->h_scalars[0];
     return SB_OK;
 }
 
 static sb_status finish_ranges(sb_sim *s, int64_t nblk, double out[4]) {
     range_final_kernel<<<1, 1024, 0, s->stream>>>(s->d_partial, nblk, s->d_scalars);
     s->launches++;
+    sb_status st = slab_allreduce(s, s->d_scalars, 4,
+                                  XR_MIN | (XR_MAX << 2) | (XR_MAX << 4) | (XR_MAX << 6));
+    if (st) return st;
     SB_CUDA(cudaMemcpyAsync(s->h_scalars, s->d_scalars, 4 * sizeof(double),
                             cudaMemcpyDeviceToHost, s->stream));
     SB_CUDA(cudaStreamSynchronize(s->stream));
@@ -620,6 +650,14 @@ sb_status launch_adapt_uv(sb_sim *s) {
         s->launches++;
     }
     SB_CUDA(cudaGetLastError());
+    if (s->slab) {
+        // new u, v of my edge rows -> the neighbours' halo rows.  The barrier in front keeps a
+        // slow neighbour's F/G pass from reading rows of the NEXT step; the range reduction
+        // below is the barrier behind the puts.
+        if ((st = slab_allreduce(s, s->d_scalars, 0, 0))) return st;
+        if ((st = slab_put_rows(s, s->u, s->lo_u, s->hi_u, 8))) return st;
+        if ((st = slab_put_rows(s, s->v, s->lo_v, s->hi_v, 8))) return st;
+    }
     double out[4];
     st = finish_ranges(s, (int64_t)gx * rows, out);
     if (st) return st;
@@ -683,6 +721,27 @@ sb_status launch_cellop(int op, const double *u9, const double *v9, const double
         return SB_CUDA_ERROR;
     }
     return SB_OK;
+}
+
+// force-load this file's kernels (CUDA loads lazily by default, and a first launch that has
+// to load code synchronises the context -- fatal while a peer slab of the same process spins
+// in an all-gather on the same GPU)
+void preload_stages() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, velocity_bc_gather);
+    cudaFuncGetAttributes(&a, velocity_bc_scatter);
+    cudaFuncGetAttributes(&a, fg_kernel);
+    cudaFuncGetAttributes(&a, rhs_kernel);
+    cudaFuncGetAttributes(&a, pressure_bc_kernel);
+    cudaFuncGetAttributes(&a, norm_partial_kernel);
+    cudaFuncGetAttributes(&a, sor_finalize_kernel);
+    cudaFuncGetAttributes(&a, sum_partials_kernel);
+    cudaFuncGetAttributes(&a, adapt_uv_kernel);
+    cudaFuncGetAttributes(&a, restore_uv_kernel);
+    cudaFuncGetAttributes(&a, range_kernel);
+    cudaFuncGetAttributes(&a, range_final_kernel);
+    cudaFuncGetAttributes(&a, cellop_kernel);
+    cudaGetLastError();
 }
 
 }  // namespace sb

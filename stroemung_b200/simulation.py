@@ -150,7 +150,7 @@ class Simulation:
             x_end=x_end, rank=rank, world=world)
 
     @classmethod
-    def try_from(cls, unfinalized, **ext):
+    def try_from(cls, unfinalized, velocity_table=None, **ext):
         """Simulation::try_from(UnfinalizedSimulation) (src/simulation.rs:71-99).
 
         `unfinalized`: dict with the fields of UnfinalizedSimulation; its "grid" is a dict
@@ -171,7 +171,15 @@ class Simulation:
         p, u, v = arr(grid.get("p")), arr(grid.get("u")), arr(grid.get("v"))
         bu = grid.get("bu") if grid.get("bu") is not None else np.zeros(kind.shape)
         bv = grid.get("bv") if grid.get("bv") is not None else np.zeros(kind.shape)
-        tab, ntab = _velocity_table(kind, bu, bv, x_offset=int(prm.x_begin) if prm.world > 1 else 0)
+        if velocity_table is not None:
+            # slab mode: the merged table of stroemung_b200.multi (own + halo rows, global x)
+            ntab = len(velocity_table)
+            tab = (_capi.BoundaryVelocity * max(ntab, 1))()
+            for i, (x, y, tu, tv) in enumerate(velocity_table):
+                tab[i] = _capi.BoundaryVelocity(int(x), int(y), float(tu), float(tv))
+        else:
+            tab, ntab = _velocity_table(kind, bu, bv,
+                                        x_offset=int(prm.x_begin) if prm.world > 1 else 0)
         h = C.c_void_p()
         st = _capi.lib().sb_create(C.byref(prm), _dp(p), _dp(u), _dp(v),
                                    kind.ctypes.data_as(C.POINTER(C.c_uint8)), tab, ntab,
@@ -198,6 +206,21 @@ class Simulation:
                                           len(preset_args), C.byref(h))
         _capi.check(st, None)
         return cls(h, prm)
+
+    # row slabs (include/stroemung_b200.h "multi-GPU"; host plumbing in multi.py) -------
+    def slab_export(self):
+        blob = (C.c_uint8 * _capi.SLAB_BLOB_BYTES)()
+        self._check(_capi.lib().sb_slab_export(self._h, blob))
+        return bytes(blob)
+
+    def slab_connect(self, blobs):
+        """collective: every rank passes all ranks' blobs in rank order"""
+        from .multi import blob_buffer
+        self._check(_capi.lib().sb_slab_connect(self._h, blob_buffer(blobs), len(blobs)))
+
+    def slab_sync_halos(self):
+        """collective: after assigning grid.pressure / u / v on any rank"""
+        self._check(_capi.lib().sb_slab_sync_halos(self._h))
 
     def close(self):
         if getattr(self, "_h", None):
