@@ -166,6 +166,7 @@ struct sb_sim {
     // neighbours' u, v, cflag arrays (halo puts outside the SOR passes)
     double *lo_u = nullptr, *lo_v = nullptr, *hi_u = nullptr, *hi_v = nullptr;
     uint8_t *lo_flag = nullptr, *hi_flag = nullptr;
+    double *lo_rhs = nullptr, *hi_rhs = nullptr;
     double *d_hist = nullptr;                 // norm history of sb_sor_sweeps (grows only)
     size_t hist_cap = 0;
     // tensor maps for the red-black pass (built lazily per buffer)

@@ -8,6 +8,8 @@
 //   p    the red-black pass writes its edge rows straight into the neighbours' halo rows
 //        (sor_rb.cu epilogue, P2P stores) -- SB_SLAB_HALO = 2T+2 rows for T = 4 fused sweeps;
 //   u, v after the velocity update, by the put kernel below;
+//   rhs  after calculate_rhs (the red-black tiles recompute their 2T+2 halo rows, so the
+//        right-hand side must be valid there too), put kernel;
 //   kind at classification time (put kernel, bytes);
 //   residual sums, min/max ranges, fluid counts: slab_allgather() (slab_dev.cuh), summed
 //        in rank order on every rank -- deterministic and identical everywhere.
@@ -35,8 +37,8 @@ struct SlabBlob {                 // what sb_slab_export writes (<= SB_SLAB_BLOB
     int32_t rank, world, device, pid;
     uint64_t host_tag;            // distinguishes processes beyond the pid (boot-unique enough)
     int64_t nxl, pitch, own0, own1, NX, NY;
-    uint64_t raw[7];              // p0, p1, u, v, cflag, mbox, (unused): same-process access
-    cudaIpcMemHandle_t ipc[6];    // p0, p1, u, v, cflag, mbox
+    uint64_t raw[7];              // p0, p1, u, v, cflag, mbox, rhs: same-process access
+    cudaIpcMemHandle_t ipc[7];    // the same allocations for other processes
 };
 static_assert(sizeof(SlabBlob) <= SB_SLAB_BLOB_BYTES, "blob must fit the ABI constant");
 constexpr uint32_t BLOB_MAGIC = 0x53423230u;  // "SB20"
@@ -208,8 +210,8 @@ sb_status sb_slab_export(sb_sim *sim, uint8_t blob[SB_SLAB_BLOB_BYTES]) {
     b.host_tag = process_tag();
     b.nxl = sim->g.nxl; b.pitch = sim->g.pitch; b.own0 = sim->g.own0; b.own1 = sim->g.own1;
     b.NX = sim->g.NX; b.NY = sim->g.NY;
-    void *ptrs[6] = {sim->p[0], sim->p[1], sim->u, sim->v, sim->cflag, sim->d_mbox};
-    for (int i = 0; i < 6; i++) {
+    void *ptrs[7] = {sim->p[0], sim->p[1], sim->u, sim->v, sim->cflag, sim->d_mbox, sim->rhs};
+    for (int i = 0; i < 7; i++) {
         b.raw[i] = (uint64_t)(uintptr_t)ptrs[i];
         SB_CUDA(cudaIpcGetMemHandle(&b.ipc[i], ptrs[i]));
     }
@@ -274,19 +276,21 @@ sb_status sb_slab_connect(sb_sim *sim, const uint8_t *blobs, size_t n_blobs) {
         lk.mbox[r] = static_cast<MailSlot *>(p);
     }
     if (me > 0) {
-        void *p[5];
-        for (int i = 0; i < 5; i++)
-            if ((st = map(me - 1, i, &p[i]))) return st;
+        void *p[7];
+        for (int i = 0; i < 7; i++)
+            if (i != 5 && (st = map(me - 1, i, &p[i]))) return st;
         lk.lo_p[0] = (double *)p[0]; lk.lo_p[1] = (double *)p[1];
         sim->lo_u = (double *)p[2]; sim->lo_v = (double *)p[3]; sim->lo_flag = (uint8_t *)p[4];
+        sim->lo_rhs = (double *)p[6];
         lk.lo_row0 = bs[me - 1].own1;  // its upper halo rows
     }
     if (me + 1 < world) {
-        void *p[5];
-        for (int i = 0; i < 5; i++)
-            if ((st = map(me + 1, i, &p[i]))) return st;
+        void *p[7];
+        for (int i = 0; i < 7; i++)
+            if (i != 5 && (st = map(me + 1, i, &p[i]))) return st;
         lk.hi_p[0] = (double *)p[0]; lk.hi_p[1] = (double *)p[1];
         sim->hi_u = (double *)p[2]; sim->hi_v = (double *)p[3]; sim->hi_flag = (uint8_t *)p[4];
+        sim->hi_rhs = (double *)p[6];
         lk.hi_row0 = bs[me + 1].own0 - lk.H;  // its lower halo rows (= 0)
     }
     sim->connected = true;

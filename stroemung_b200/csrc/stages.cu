@@ -571,6 +571,14 @@ sb_status launch_rhs(sb_sim *s) {
         s->g, s->f, s->gq, s->rhs, row0, row1, s->prm.delx, s->prm.dely, s->prm.delt);
     s->launches++;
     SB_CUDA(cudaGetLastError());
+    if (s->slab) {
+        // the red-black tiles re-sweep their halo rows and need rhs there: edge rows -> the
+        // neighbours' halo rows, then a barrier before the first pass reads them.  (The
+        // neighbours left their previous solve long ago: the barriers of the velocity update.)
+        sb_status st = slab_put_rows(s, s->rhs, s->lo_rhs, s->hi_rhs, 8);
+        if (st) return st;
+        return slab_allreduce(s, s->d_scalars, 0, 0);
+    }
     return SB_OK;
 }
 
