@@ -227,7 +227,19 @@ def run_ours(args):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout at the first communicator: keep stdout
+        # clean for the ONE JSON line by pointing fd 1 at stderr until NCCL is up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     n_gpus = world
     wl = workload(args.workload, n_gpus, args.size)
     nx, ny = wl["size"]

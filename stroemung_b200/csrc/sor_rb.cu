@@ -338,7 +338,9 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-template <int PAR>
+// SLAB: this handle is one row slab of a multi-GPU run (own rows inside halo rows, neighbours
+// to feed).  The single-GPU instantiation carries none of that code.
+template <int PAR, bool SLAB>
 __global__ void __launch_bounds__(NTHR, 2)
 sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__ CUtensorMap tm_p1,
               const __grid_constant__ CUtensorMap tm_rhs, const uint8_t *__restrict__ cflag,
@@ -360,7 +362,7 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
 
     const int BX = TXR - 2 * h, BY = TW - 2 * h;  // h is even: owned columns 16-byte aligned
     const int tile_i = blockIdx.x / tiles_y, tile_j = blockIdx.x - tile_i * tiles_y;
-    const int tx0 = (int)g.own0 + tile_i * BX - h;  // local row of tile row 0 (even)
+    const int tx0 = (SLAB ? (int)g.own0 : 0) + tile_i * BX - h;  // local row of tile row 0 (even)
     const int ty0 = tile_j * BY - h;   // column of tile column 0 (even)
 
     if (threadIdx.x == 0) {
@@ -401,7 +403,8 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
         // stored: the exact inner rows this slab owns (its halo rows belong to the neighbours,
         // who write them from their own epilogue below)
         const uint32_t rows_st =
-            row_bits(max(max(in_lo, own_lo), h), min(min(in_hi, own_hi), TXR - h), r_begin);
+            SLAB ? row_bits(max(max(in_lo, own_lo), h), min(min(in_hi, own_hi), TXR - h), r_begin)
+                 : row_bits(max(in_lo, h), min(in_hi, TXR - h), r_begin);
         // column properties of the two cells -> 0x555555 / 0xAAAAAA patterns
         uint32_t cols_upd = 0, cols_cnt = 0, cols_bc = 0;
 #pragma unroll
@@ -564,25 +567,32 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
         }
         // halo exchange fused into the pass: rows within H of a slab edge also go straight
         // into the neighbour's halo rows of ITS target buffer (P2P stores over NVLink); the
-        // all-gather of the finalize kernel that follows is the release/acquire point
-        if (peers.lo_p[0] || peers.hi_p[0]) {
-            const int lx0 = tx0 + r_begin;
+        // all-gather of the finalize kernel that follows is the release/acquire point.  Only
+        // the first and last tile rows of a slab ever get here (block-uniform test).
+        if (SLAB) {
             const int own0 = (int)g.own0, own1 = (int)g.own1;
+            const bool lo_tile = peers.lo_p[0] != nullptr && tx0 + h < own0 + peers.H;
+            const bool hi_tile = peers.hi_p[0] != nullptr && tx0 + TXR - h > own1 - peers.H;
+            if (lo_tile || hi_tile) {
+                double *lo = src ? peers.lo_p[0] : peers.lo_p[1];
+                double *hi = src ? peers.hi_p[0] : peers.hi_p[1];
+                const int lx0 = tx0 + r_begin;
+                lo += (peers.lo_row0 + (lx0 - own0)) * g.pitch + gy0;
+                hi += (peers.hi_row0 + (lx0 - (own1 - peers.H))) * g.pitch + gy0;
 #pragma unroll
-            for (int i = 0; i < RPT; i++) {
-                if (!(m_store & (1u << (2 * i)))) continue;
-                const int lx = lx0 + i;
-                if (peers.lo_p[0] && lx < own0 + peers.H) {
-                    double *dst = peers.lo_p[src ^ 1] +
-                                  (peers.lo_row0 + (lx - own0)) * g.pitch + gy0;
-                    if (pair) *reinterpret_cast<double2 *>(dst) = P[i];
-                    else dst[0] = P[i].x;
-                }
-                if (peers.hi_p[0] && lx >= own1 - peers.H) {
-                    double *dst = peers.hi_p[src ^ 1] +
-                                  (peers.hi_row0 + (lx - (own1 - peers.H))) * g.pitch + gy0;
-                    if (pair) *reinterpret_cast<double2 *>(dst) = P[i];
-                    else dst[0] = P[i].x;
+                for (int i = 0; i < RPT; i++) {
+                    if (!(m_store & (1u << (2 * i)))) continue;
+                    const int lx = lx0 + i;
+                    if (lo_tile && lx < own0 + peers.H) {
+                        double *dst = lo + (int64_t)i * g.pitch;
+                        if (pair) *reinterpret_cast<double2 *>(dst) = P[i];
+                        else dst[0] = P[i].x;
+                    }
+                    if (hi_tile && lx >= own1 - peers.H) {
+                        double *dst = hi + (int64_t)i * g.pitch;
+                        if (pair) *reinterpret_cast<double2 *>(dst) = P[i];
+                        else dst[0] = P[i].x;
+                    }
                 }
             }
         }
@@ -634,10 +644,14 @@ sb_status ensure_tmaps(sb_sim *s) {
         if ((st = make_map(fn, &s->tm_p[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, s->p[i], s->g)))
             return st;
     if ((st = make_map(fn, &s->tm_rhs, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, s->rhs, s->g))) return st;
-    SB_CUDA(cudaFuncSetAttribute(sor_rb_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)SMEM_BYTES));
-    SB_CUDA(cudaFuncSetAttribute(sor_rb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)SMEM_BYTES));
+    SB_CUDA(cudaFuncSetAttribute(sor_rb_kernel<0, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SB_CUDA(cudaFuncSetAttribute(sor_rb_kernel<1, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SB_CUDA(cudaFuncSetAttribute(sor_rb_kernel<0, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SB_CUDA(cudaFuncSetAttribute(sor_rb_kernel<1, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     s->tmaps_ready = true;
     return SB_OK;
 }
@@ -685,14 +699,11 @@ sb_status launch_sor_rb_pass(sb_sim *s, int *ntiles_out, int norm_only) {
     // the parity of the slab's global row offset
     const int par = (int)(((g.gx0 % 2) + 2) % 2);
     if (!norm_only) prof_mark(s);
-    if (par)
-        sor_rb_kernel<1><<<ntiles, NTHR, SMEM_BYTES, s->stream>>>(
-            s->tm_p[0], s->tm_p[1], s->tm_rhs, s->cflag, g, pbuf_ptr(s), s->d_ctl, s->d_partial,
-            tiles_y, ntiles, h, k, norm_only, peers);
-    else
-        sor_rb_kernel<0><<<ntiles, NTHR, SMEM_BYTES, s->stream>>>(
-            s->tm_p[0], s->tm_p[1], s->tm_rhs, s->cflag, g, pbuf_ptr(s), s->d_ctl, s->d_partial,
-            tiles_y, ntiles, h, k, norm_only, peers);
+    auto kern = s->slab ? (par ? sor_rb_kernel<1, true> : sor_rb_kernel<0, true>)
+                        : (par ? sor_rb_kernel<1, false> : sor_rb_kernel<0, false>);
+    kern<<<ntiles, NTHR, SMEM_BYTES, s->stream>>>(s->tm_p[0], s->tm_p[1], s->tm_rhs, s->cflag, g,
+                                                  pbuf_ptr(s), s->d_ctl, s->d_partial, tiles_y,
+                                                  ntiles, h, k, norm_only, peers);
     if (!norm_only) prof_mark(s);
     s->launches++;
     SB_CUDA(cudaGetLastError());
@@ -705,8 +716,10 @@ sb_status launch_sor_rb_pass(sb_sim *s, int *ntiles_out, int norm_only) {
 // in an all-gather on the same GPU)
 void preload_sor_rb() {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, sor_rb_kernel<0>);
-    cudaFuncGetAttributes(&a, sor_rb_kernel<1>);
+    cudaFuncGetAttributes(&a, sor_rb_kernel<0, false>);
+    cudaFuncGetAttributes(&a, sor_rb_kernel<1, false>);
+    cudaFuncGetAttributes(&a, sor_rb_kernel<0, true>);
+    cudaFuncGetAttributes(&a, sor_rb_kernel<1, true>);
     cudaGetLastError();
 }
 
