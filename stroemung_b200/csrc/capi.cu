@@ -228,8 +228,7 @@ sb_status finish_create(sb_sim *s) {
     if ((st = sync_ctl_idle(s))) return st;
     if ((st = launch_pressure_range(s))) return st;
     if ((st = launch_speed_range(s))) return st;
-    if ((st = launch_fg(s))) return st;
-    if ((st = launch_rhs(s))) return st;
+    if ((st = launch_fg_rhs(s, 3))) return st;
     if (!s->has_initial_norm) {
         double n = 0.0;
         if ((st = norm_now(s, &n))) return st;
@@ -348,8 +347,7 @@ static sb_status tick(sb_sim *s, uint32_t *iters, double *norm) {
     sb_status st;
     if (s->prm.tau > 0.0) adapt_delt(s);
     if ((st = launch_velocity_bc(s))) return st;
-    if ((st = launch_fg(s))) return st;
-    if ((st = launch_rhs(s))) return st;
+    if ((st = launch_fg_rhs(s, 3))) return st;
     if ((st = solve(s, s->prm.max_iterations, 1, iters, norm, nullptr))) return st;
     if ((st = launch_adapt_uv(s))) return st;
     s->time += s->prm.delt;

@@ -10,63 +10,143 @@
 // ["north" is j-1, src/grid/mod.rs:168-176].
 #pragma once
 
+#include <math.h>
+
 namespace sb {
 
+// ---- division by a per-launch constant ----------------------------------------------------
+// Every `/` of the reference on this path divides by a run constant (dx*dx, 4*dx, Re, dt ...).
+// nvcc's correctly rounded f64 division is a ~25-instruction routine, most of it spent on the
+// reciprocal; with the divisor fixed the reciprocal is hoisted to the host and the quotient
+// is finished with Markstein's correction steps:
+//     q0 = a*r;  e0 = fma(-d, q0, a);  q1 = fma(e0, r, q0)        (q1 is a faithful quotient)
+//                e1 = fma(-d, q1, a);  q  = fma(e1, r, q1)        (= RN(a/d))
+// With r = RN(1/d) and q1 faithful the last step yields the correctly rounded quotient
+// (Markstein 1990; Muller et al., Handbook of Floating-Point Arithmetic, thm. 4.8), i.e. the
+// SAME BITS as the IEEE division of the Rust source.  The proof needs: no over/underflow in
+// the intermediates and the significand of d not all ones.  make_divc() checks d on the host,
+// div() checks a per call and falls back to the true division outside the safe exponent
+// window (and returns signed zeros directly).  oracle/fastdiv_check.c brute-forces the
+// equality on the CPU; the GPU parity tests compare every field bit for bit with the oracle,
+// which uses the plain `/`.
+struct DivC {
+    double d;   // the divisor
+    double r;   // RN(1/d)
+    int fast;   // correction-step path allowed for this divisor
+    __device__ __forceinline__ double operator()(double a) const {
+        if (fast) {
+            const double aa = fabs(a);
+            if (aa >= 0x1p-450 && aa <= 0x1p450) {
+                double q = a * r;
+                double e = fma(-d, q, a);
+                q = fma(e, r, q);
+                e = fma(-d, q, a);
+                return fma(e, r, q);
+            }
+            if (a == 0.0) return d > 0.0 ? a : -a;
+        }
+        return a / d;
+    }
+};
+
+// The same correction steps without a branch per division: the operand check (exponent
+// inside the safe window, or an exact zero) is accumulated into *bad with integer
+// instructions and the caller redoes the whole cell with plain divisions if it ever fires.
+// The sign of a zero quotient is taken from q0 = a*r (the fma chain would give +0 for -0).
+struct DivF {
+    double d, r;
+    unsigned *bad;
+    __device__ __forceinline__ double operator()(double a) const {
+        const int hi = __double2hiint(a);
+        const unsigned e = ((unsigned)hi >> 20) & 0x7ffu;
+        const bool ok = (e - 573u) <= 900u || (((unsigned)hi << 1) | (unsigned)__double2loint(a)) == 0u;
+        *bad |= ok ? 0u : 1u;
+        const double q0 = a * r;
+        double er = fma(-d, q0, a);
+        double q = fma(er, r, q0);
+        er = fma(-d, q, a);
+        q = fma(er, r, q);
+        return q == 0.0 ? q0 : q;
+    }
+};
+
+// plain IEEE division (known-answer entry points, one-off uses)
+struct DivT {
+    double d;
+    __device__ __forceinline__ double operator()(double a) const { return a / d; }
+};
+
+inline DivC make_divc(double d) {
+    DivC c;
+    c.d = d;
+    c.r = 1.0 / d;
+    int ex = 0;
+    const double m = frexp(fabs(d), &ex);  // m in [0.5, 1)
+    c.fast = isfinite(d) && d != 0.0 && ex > -400 && ex < 400 && m != 0x1.fffffffffffffp-1;
+    return c;
+}
+
 // src/math.rs:19-33
-__device__ __forceinline__ double du2dx(double u_w, double u_c, double u_e, double delx,
+template <class D4>
+__device__ __forceinline__ double du2dx(double u_w, double u_c, double u_e, const D4 &four_delx,
                                         double gamma) {
     double a = u_c + u_e, b = u_w + u_c;
     double left_side = (a * a) - (b * b);
     double inner_left2 = fabs(a) * (u_c - u_e);
     double inner_right2 = fabs(b) * (u_w - u_c);
-    return (left_side + (gamma * (inner_left2 - inner_right2))) / (4.0 * delx);
+    return four_delx(left_side + (gamma * (inner_left2 - inner_right2)));
 }
 
 // src/math.rs:53-77
+template <class D4>
 __device__ __forceinline__ double duvdx(double u_c, double u_s, double u_w, double u_sw,
-                                        double v_c, double v_e, double v_w, double delx,
+                                        double v_c, double v_e, double v_w, const D4 &four_delx,
                                         double gamma) {
     double a = u_c + u_s, b = u_w + u_sw;
     double left_side = (a * (v_c + v_e)) - (b * (v_w + v_c));
     double inner_left2 = fabs(a) * (v_c - v_e);
     double inner_right2 = fabs(b) * (v_w - v_c);
-    return (left_side + (gamma * (inner_left2 - inner_right2))) / (4.0 * delx);
+    return four_delx(left_side + (gamma * (inner_left2 - inner_right2)));
 }
 
 // src/math.rs:97-120
+template <class D4>
 __device__ __forceinline__ double duvdy(double u_c, double u_n, double u_s, double v_c,
-                                        double v_n, double v_e, double v_ne, double dely,
+                                        double v_n, double v_e, double v_ne, const D4 &four_dely,
                                         double gamma) {
     double a = v_c + v_e, b = v_n + v_ne;
     double left_side = (a * (u_c + u_s)) - (b * (u_n + u_c));
     double inner_left2 = fabs(a) * (u_c - u_s);
     double inner_right2 = fabs(b) * (u_n - u_c);
-    return (left_side + (gamma * (inner_left2 - inner_right2))) / (4.0 * dely);
+    return four_dely(left_side + (gamma * (inner_left2 - inner_right2)));
 }
 
 // src/math.rs:136-150
-__device__ __forceinline__ double dv2dy(double v_n, double v_c, double v_s, double dely,
+template <class D4>
+__device__ __forceinline__ double dv2dy(double v_n, double v_c, double v_s, const D4 &four_dely,
                                         double gamma) {
     double a = v_c + v_s, b = v_n + v_c;
     double left_side = (a * a) - (b * b);
     double inner_left2 = fabs(a) * (v_c - v_s);
     double inner_right2 = fabs(b) * (v_n - v_c);
-    return (left_side + (gamma * (inner_left2 - inner_right2))) / (4.0 * dely);
+    return four_dely(left_side + (gamma * (inner_left2 - inner_right2)));
 }
 
-// src/math.rs:162-174
+// src/math.rs:162-174; dx2 / dy2 divide by (delx * delx) / (dely * dely)
+template <class D2>
 __device__ __forceinline__ double laplacian(double e_c, double e_n, double e_s, double e_w,
-                                            double e_e, double delx, double dely) {
-    double d2edx2 = ((e_e - (2. * e_c)) + e_w) / (delx * delx);
-    double d2edy2 = ((e_s - (2. * e_c)) + e_n) / (dely * dely);
+                                            double e_e, const D2 &dx2, const D2 &dy2) {
+    double d2edx2 = dx2((e_e - (2. * e_c)) + e_w);
+    double d2edy2 = dy2((e_s - (2. * e_c)) + e_n);
     return d2edx2 + d2edy2;
 }
 
 // src/math.rs:176-186
+template <class D2>
 __device__ __forceinline__ double residual(double p_c, double p_n, double p_s, double p_w,
-                                           double p_e, double delx, double dely, double rhs) {
-    double part1 = ((p_e - p_c) - (p_c - p_w)) / (delx * delx);
-    double part2 = ((p_s - p_c) - (p_c - p_n)) / (dely * dely);
+                                           double p_e, const D2 &dx2, const D2 &dy2, double rhs) {
+    double part1 = dx2((p_e - p_c) - (p_c - p_w));
+    double part2 = dy2((p_s - p_c) - (p_c - p_n));
     return (part1 + part2) - rhs;
 }
 
@@ -75,22 +155,39 @@ struct Stencil9 {
     double c, n, s, w, e, nw, ne, sw, se;
 };
 
+// the run constants every F / G evaluation divides by
+template <class D>
+struct FgDiv {
+    D dx2, dy2;          // delx * delx, dely * dely   (laplacian)
+    D four_dx, four_dy;  // 4.0 * delx, 4.0 * dely     (du2dx, duvdx / duvdy, dv2dy)
+    D re;                // reynolds
+};
+
+template <class D>
+__host__ __device__ inline FgDiv<D> fg_div_plain(double delx, double dely, double reynolds) {
+    FgDiv<D> k;
+    k.dx2.d = delx * delx; k.dy2.d = dely * dely;
+    k.four_dx.d = 4.0 * delx; k.four_dy.d = 4.0 * dely;
+    k.re.d = reynolds;
+    return k;
+}
+
 // src/simulation.rs:349-363
-__device__ __forceinline__ double calculate_f(const Stencil9 &u, const Stencil9 &v, double delx,
-                                              double dely, double delt, double gamma,
-                                              double reynolds) {
-    return u.c + (delt * (((laplacian(u.c, u.n, u.s, u.w, u.e, delx, dely) / reynolds) -
-                           du2dx(u.w, u.c, u.e, delx, gamma)) -
-                          duvdy(u.c, u.n, u.s, v.c, v.n, v.e, v.ne, dely, gamma)));
+template <class D>
+__device__ __forceinline__ double calculate_f(const Stencil9 &u, const Stencil9 &v,
+                                              const FgDiv<D> &k, double delt, double gamma) {
+    return u.c + (delt * ((k.re(laplacian(u.c, u.n, u.s, u.w, u.e, k.dx2, k.dy2)) -
+                           du2dx(u.w, u.c, u.e, k.four_dx, gamma)) -
+                          duvdy(u.c, u.n, u.s, v.c, v.n, v.e, v.ne, k.four_dy, gamma)));
 }
 
 // src/simulation.rs:378-392
-__device__ __forceinline__ double calculate_g(const Stencil9 &u, const Stencil9 &v, double delx,
-                                              double dely, double delt, double gamma,
-                                              double reynolds) {
-    return v.c + (delt * (((laplacian(v.c, v.n, v.s, v.w, v.e, delx, dely) / reynolds) -
-                           duvdx(u.c, u.s, u.w, u.sw, v.c, v.e, v.w, delx, gamma)) -
-                          dv2dy(v.n, v.c, v.s, dely, gamma)));
+template <class D>
+__device__ __forceinline__ double calculate_g(const Stencil9 &u, const Stencil9 &v,
+                                              const FgDiv<D> &k, double delt, double gamma) {
+    return v.c + (delt * ((k.re(laplacian(v.c, v.n, v.s, v.w, v.e, k.dx2, k.dy2)) -
+                           duvdx(u.c, u.s, u.w, u.sw, v.c, v.e, v.w, k.four_dx, gamma)) -
+                          dv2dy(v.n, v.c, v.s, k.four_dy, gamma)));
 }
 
 // view[(a, b)] == blk[3*a + b]: a indexes x (w, c, e), b indexes y (n, c, s)

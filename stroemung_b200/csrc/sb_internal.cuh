@@ -183,6 +183,7 @@ sb_status apply_velocity_table(sb_sim *s);     // scatter sparse (x,y,u,v) into 
 // stages.cu
 sb_status launch_velocity_bc(sb_sim *s);
 sb_status launch_fg(sb_sim *s);
+sb_status launch_fg_rhs(sb_sim *s, int what);  // 1: F, G; 3: F, G and RHS fused
 sb_status launch_rhs(sb_sim *s);
 sb_status launch_pressure_bc(sb_sim *s, int guarded);
 sb_status launch_norm_partials(sb_sim *s, int guarded, int *nblocks);

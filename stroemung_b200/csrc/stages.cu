@@ -156,63 +156,181 @@ __global__ void velocity_bc_scatter(Geom g, double *__restrict__ u, double *__re
     }
 }
 
-// ---- K2: F and G ------------------------------------------------------------------------
-// All interior cells get the stencil value (fluid or not); afterwards the reference
+// ---- K2: F, G and RHS in one pass -------------------------------------------------------------
+// F, G: all interior cells get the stencil value (fluid or not); afterwards the reference
 // overwrites f[b]=u[b], g[b]=v[b] on every boundary cell and g[n]=v[n] / f[w]=u[w] on the
 // fluid cell north / west of one (src/simulation.rs:167-201).  Per cell that is:
 //   non-fluid c                       -> f = u[c], g = v[c]
 //   fluid c with (x+1, y) non-fluid   -> f = u[c]   (c is that cell's west neighbour)
 //   fluid c with (x, y+1) non-fluid   -> g = v[c]   (c is that cell's north neighbour)
-// Ring cells are outside the stencil loop: they only receive the overwrites.
-__global__ void fg_kernel(Geom g, const double *__restrict__ u, const double *__restrict__ v,
-                          const uint8_t *__restrict__ cflag, double *__restrict__ f,
-                          double *__restrict__ gq, int64_t row0, int64_t row1, double delx,
-                          double dely, double delt, double gamma, double reynolds) {
-    int64_t y = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
-    int64_t lx = row0 + blockIdx.x;
-    if (y >= g.NY || lx >= row1) return;
-    int64_t gx = g.gx0 + lx;
-    if (gx < 0 || gx >= g.NX) return;
-    int64_t c = lx * g.pitch + y;
-    uint8_t fl = cflag[c];
-    bool interior = gx >= 1 && gx <= g.NX - 2 && y >= 1 && y <= g.NY - 2;
-    if (!cf_is_fluid(fl)) {
-        f[c] = u[c];
-        gq[c] = v[c];
-        return;
-    }
-    bool east_solid = gx + 1 < g.NX && lx + 1 < g.nxl && !cf_is_fluid(cflag[c + g.pitch]);
-    bool south_solid = y + 1 < g.NY && !cf_is_fluid(cflag[c + 1]);
-    double fv = 0.0, gv = 0.0;
-    if (interior && !(east_solid && south_solid)) {
-        Stencil9 su, sv;
-        int64_t w = c - g.pitch, e = c + g.pitch;
-        su.nw = u[w - 1]; su.w = u[w]; su.sw = u[w + 1];
-        su.n = u[c - 1];  su.c = u[c]; su.s = u[c + 1];
-        su.ne = u[e - 1]; su.e = u[e]; su.se = u[e + 1];
-        sv.nw = v[w - 1]; sv.w = v[w]; sv.sw = v[w + 1];
-        sv.n = v[c - 1];  sv.c = v[c]; sv.s = v[c + 1];
-        sv.ne = v[e - 1]; sv.e = v[e]; sv.se = v[e + 1];
-        if (!east_solid) fv = calculate_f(su, sv, delx, dely, delt, gamma, reynolds);
-        if (!south_solid) gv = calculate_g(su, sv, delx, dely, delt, gamma, reynolds);
-    }
-    if (east_solid) f[c] = u[c];
-    else if (interior) f[c] = fv;
-    if (south_solid) gq[c] = v[c];
-    else if (interior) gq[c] = gv;
+// Ring cells are outside the stencil loop: they only receive the overwrites (a fluid ring cell
+// keeps whatever f, g it had).
+// RHS (src/simulation.rs:204-214), all cells with x >= 1 and y >= 1, fluid or not:
+//   rhs = (((f[x][y] - f[x-1][y]) / dx) + ((g[x][y] - g[x][y-1]) / dy)) / dt
+//
+// One warp owns 31 output columns (lane 0 is a helper that only produces G of the column to
+// the left, which lane 1 needs for its rhs) and marches FGR_ROWS rows along x with a 3-row
+// register window of u and v: 6 loads per cell instead of 18, F of the previous row stays in
+// a register for the rhs, G of the north neighbour comes by one shuffle.  The row in front
+// of the strip is evaluated for F only.  All divisions are by run constants (DivC).
+constexpr int FGR_ROWS = 32;
+constexpr int FGR_WARPS = 8;
+constexpr int FGR_COLS = 31 * FGR_WARPS;  // output columns per block
+
+struct FgrConsts {
+    // divisors and their reciprocals: dx*dx, dy*dy, 4dx, 4dy, Re, dx, dy, dt
+    double d[8], r[8];
+    int fast;  // every divisor qualifies for the correction-step path (make_divc)
+    double delt, gamma;
+};
+
+template <class D>
+struct FgrDiv {
+    FgDiv<D> k;
+    D dx, dy, dt;
+};
+
+// F, G (final values incl. the boundary overwrites) of one fluid interior cell and, from
+// them, its rhs; `D` decides how the 13 divisions are carried out
+template <class D>
+__device__ __forceinline__ void fgr_cell(const Stencil9 &su, const Stencil9 &sv,
+                                         const FgrDiv<D> &dv, double delt, double gamma,
+                                         bool need_f, bool need_g, double &fv, double &gv) {
+    if (need_f) fv = calculate_f(su, sv, dv.k, delt, gamma);
+    if (need_g) gv = calculate_g(su, sv, dv.k, delt, gamma);
 }
 
-// ---- RHS: all cells with x >= 1 and y >= 1, fluid or not (src/simulation.rs:204-214) ----
+__global__ void __launch_bounds__(32 * FGR_WARPS, 3)
+fg_rhs_kernel(Geom g, const double *__restrict__ u, const double *__restrict__ v,
+              const uint8_t *__restrict__ cflag, double *__restrict__ f, double *__restrict__ gq,
+              double *__restrict__ rhs, int64_t fg_row0, int64_t row1, int64_t rhs_row0,
+              FgrConsts kc, int write_fg, int write_rhs) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t y = (int64_t)blockIdx.y * FGR_COLS - 1 + (int64_t)warp * 31 + lane;
+    const int64_t xs = fg_row0 + (int64_t)blockIdx.x * FGR_ROWS;  // first output row
+    const int64_t xe = min(xs + (int64_t)FGR_ROWS, row1);
+    if (y - lane >= g.NY) return;  // warp-uniform: nothing of this warp is inside the grid
+    const bool y_ok = y >= 0 && y < g.NY;
+    const bool out_lane = lane >= 1 && y_ok;
+    // clamped column indices: loads stay inside the row, clamped values are never used by a
+    // cell that takes the stencil (those have all eight neighbours)
+    const int64_t yc = min(max(y, (int64_t)0), g.NY - 1);
+    const int64_t yn = max(yc - 1, (int64_t)0), ys = min(yc + 1, g.NY - 1);
+    const bool has_s = y + 1 < g.NY;
+    const int64_t last = g.nxl - 1;
+    auto rowp = [&](int64_t lx) { return min(max(lx, (int64_t)0), last) * g.pitch; };
+
+    unsigned bad = 0;
+    FgrDiv<DivF> df;
+    {
+        DivF *slots[8] = {&df.k.dx2, &df.k.dy2, &df.k.four_dx, &df.k.four_dy, &df.k.re,
+                          &df.dx,    &df.dy,    &df.dt};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            slots[i]->d = kc.d[i];
+            slots[i]->r = kc.r[i];
+            slots[i]->bad = &bad;
+        }
+    }
+    FgrDiv<DivT> dt_;
+    dt_.k.dx2.d = kc.d[0]; dt_.k.dy2.d = kc.d[1]; dt_.k.four_dx.d = kc.d[2];
+    dt_.k.four_dy.d = kc.d[3]; dt_.k.re.d = kc.d[4];
+    dt_.dx.d = kc.d[5]; dt_.dy.d = kc.d[6]; dt_.dt.d = kc.d[7];
+    const bool fast = kc.fast != 0;
+
+    // the pre-row (xs - 1) is needed when this strip produces rhs for row xs
+    const bool pre = write_rhs && xs >= rhs_row0 && xs - 1 >= 0;
+    int64_t x = pre ? xs - 1 : xs;
+    // window rows: 0 = x-1, 1 = x, 2 = x+1, 3 = x+2 (in flight);  columns n, c, s
+    double un[4], uc[4], us[4], vn[4], vc[4], vs[4];
+    uint8_t fl_c[4], fl_s[4];  // flags of (row, y) and (row, y+1); index 0 unused
+    auto load_row = [&](int k, int64_t lx) {
+        const int64_t r = rowp(lx);
+        un[k] = u[r + yn]; uc[k] = u[r + yc]; us[k] = u[r + ys];
+        vn[k] = v[r + yn]; vc[k] = v[r + yc]; vs[k] = v[r + ys];
+        const bool in = lx >= 0 && lx < g.nxl;
+        fl_c[k] = in ? cflag[r + yc] : (uint8_t)0;
+        fl_s[k] = (in && has_s) ? cflag[r + ys] : (uint8_t)0;
+    };
+    load_row(0, x - 1);
+    load_row(1, x);
+    load_row(2, x + 1);
+    double f_west = 0.0;  // final f of (x-1, y)
+    for (; x < xe; x++) {
+        load_row(3, x + 2);  // consumed in the next iteration: a full row of compute hides it
+
+        const int64_t gx = g.gx0 + x;
+        const int64_t c = x * g.pitch + yc;
+        const uint8_t fl = fl_c[1];
+        const bool valid = y_ok && (fl & CF_VALID);
+        const bool interior = gx >= 1 && gx <= g.NX - 2 && y >= 1 && y <= g.NY - 2;
+        const bool want_rhs = write_rhs && x >= xs && x >= rhs_row0 && gx >= 1 && y >= 1;
+        double fv = 0.0, gv = 0.0;
+        bool st_f = false, st_g = false, need_f = false, need_g = false;
+        if (valid) {
+            if (!cf_is_fluid(fl)) {
+                fv = uc[1];
+                gv = vc[1];
+                st_f = st_g = true;
+            } else {
+                const bool east_solid = gx + 1 < g.NX && x + 1 < g.nxl && !cf_is_fluid(fl_c[2]);
+                const bool south_solid = has_s && !cf_is_fluid(fl_s[1]);
+                if (east_solid) { fv = uc[1]; st_f = true; }
+                else if (interior) { need_f = st_f = true; }
+                else fv = f[c];   // fluid ring cell: untouched by the reference
+                if (south_solid) { gv = vc[1]; st_g = true; }
+                else if (interior) { need_g = st_g = true; }
+                else gv = gq[c];
+            }
+        }
+        Stencil9 su, sv;
+        su.nw = un[0]; su.w = uc[0]; su.sw = us[0];
+        su.n = un[1];  su.c = uc[1]; su.s = us[1];
+        su.ne = un[2]; su.e = uc[2]; su.se = us[2];
+        sv.nw = vn[0]; sv.w = vc[0]; sv.sw = vs[0];
+        sv.n = vn[1];  sv.c = vc[1]; sv.s = vs[1];
+        sv.ne = vn[2]; sv.e = vc[2]; sv.se = vs[2];
+        double rv = 0.0;
+        bad = fast ? 0u : 1u;
+        if (fast) {
+            fgr_cell(su, sv, df, kc.delt, kc.gamma, need_f, need_g, fv, gv);
+            const double g_north = __shfl_up_sync(0xffffffffu, gv, 1);
+            rv = df.dt(df.dx(fv - f_west) + df.dy(gv - g_north));
+        }
+        // rare: an operand outside the safe exponent window somewhere in this warp's row --
+        // every lane redoes its cell with plain IEEE divisions (the shuffle needs all lanes)
+        if (__any_sync(0xffffffffu, bad != 0u)) {
+            fgr_cell(su, sv, dt_, kc.delt, kc.gamma, need_f, need_g, fv, gv);
+            const double g_north = __shfl_up_sync(0xffffffffu, gv, 1);
+            rv = dt_.dt(dt_.dx(fv - f_west) + dt_.dy(gv - g_north));
+        }
+        if (x >= xs && out_lane && valid) {  // not the pre-row
+            if (write_fg && st_f) f[c] = fv;
+            if (write_fg && st_g) gq[c] = gv;
+            if (want_rhs) rhs[c] = rv;
+        }
+        f_west = fv;
+        // slide the window
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            un[k] = un[k + 1]; uc[k] = uc[k + 1]; us[k] = us[k + 1];
+            vn[k] = vn[k + 1]; vc[k] = vc[k + 1]; vs[k] = vs[k + 1];
+            fl_c[k] = fl_c[k + 1]; fl_s[k] = fl_s[k + 1];
+        }
+    }
+}
+
+// RHS on its own (sb_calculate_rhs): reads f, g from memory
 __global__ void rhs_kernel(Geom g, const double *__restrict__ f, const double *__restrict__ gq,
-                           double *__restrict__ rhs, int64_t row0, int64_t row1, double delx,
-                           double dely, double delt) {
+                           double *__restrict__ rhs, int64_t row0, int64_t row1, DivC dx,
+                           DivC dy, DivC dt) {
     int64_t y = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     int64_t lx = row0 + blockIdx.x;
     if (y < 1 || y >= g.NY || lx >= row1) return;
     int64_t gx = g.gx0 + lx;
     if (gx < 1 || gx >= g.NX) return;
     int64_t c = lx * g.pitch + y;
-    rhs[c] = (((f[c] - f[c - g.pitch]) / delx) + ((gq[c] - gq[c - 1]) / dely)) / delt;
+    rhs[c] = dt(dx(f[c] - f[c - g.pitch]) + dy(gq[c] - gq[c - 1]));
 }
 
 // ---- K3: pressure BC over the boundary list (reads fluid cells, writes boundary cells) ---
@@ -246,7 +364,7 @@ constexpr int NORM_ROWS_PER_BLOCK = 4;
 __global__ void norm_partial_kernel(Geom g, double *const *__restrict__ pbuf,
                                     const SorCtl *__restrict__ ctl, int guarded,
                                     const double *__restrict__ rhs, double *__restrict__ partial,
-                                    double delx, double dely) {
+                                    DivC dx2, DivC dy2) {
     if (guarded && ctl->active_T == 0) return;
     const double *p = pbuf[ctl->src];
     double acc = 0.0;
@@ -258,8 +376,8 @@ __global__ void norm_partial_kernel(Geom g, double *const *__restrict__ pbuf,
         for (int64_t y = 1 + (int64_t)blockIdx.y * blockDim.x + threadIdx.x; y <= g.NY - 2;
              y += (int64_t)gridDim.y * blockDim.x) {
             int64_t c = lx * g.pitch + y;
-            double rr = residual(p[c], p[c - 1], p[c + 1], p[c - g.pitch], p[c + g.pitch], delx,
-                                 dely, rhs[c]);
+            double rr = residual(p[c], p[c - 1], p[c + 1], p[c - g.pitch], p[c + g.pitch], dx2,
+                                 dy2, rhs[c]);
             acc = acc + (rr * rr);
         }
     }
@@ -507,14 +625,17 @@ __global__ void cellop_kernel(int op, const double *__restrict__ in, double *__r
     Stencil9 su = stencil_from_block(ub), sv = stencil_from_block(vb);
     double r = 0.0;
     switch (op) {
-    case 0: r = du2dx(su.w, su.c, su.e, sc[0], sc[1]); break;                     // delx, gamma
-    case 1: r = duvdx(su.c, su.s, su.w, su.sw, sv.c, sv.e, sv.w, sc[0], sc[1]); break;
-    case 2: r = duvdy(su.c, su.n, su.s, sv.c, sv.n, sv.e, sv.ne, sc[0], sc[1]); break;  // dely
-    case 3: r = dv2dy(sv.n, sv.c, sv.s, sc[0], sc[1]); break;
-    case 4: r = laplacian(su.c, su.n, su.s, su.w, su.e, sc[0], sc[1]); break;     // delx, dely
-    case 5: r = residual(su.c, su.n, su.s, su.w, su.e, sc[0], sc[1], sc[2]); break;
-    case 6: r = calculate_f(su, sv, sc[0], sc[1], sc[2], sc[3], sc[4]); break;
-    case 7: r = calculate_g(su, sv, sc[0], sc[1], sc[2], sc[3], sc[4]); break;
+    // plain IEEE division here: these entry points pin the operators themselves
+    case 0: r = du2dx(su.w, su.c, su.e, DivT{4.0 * sc[0]}, sc[1]); break;         // delx, gamma
+    case 1: r = duvdx(su.c, su.s, su.w, su.sw, sv.c, sv.e, sv.w, DivT{4.0 * sc[0]}, sc[1]); break;
+    case 2: r = duvdy(su.c, su.n, su.s, sv.c, sv.n, sv.e, sv.ne, DivT{4.0 * sc[0]}, sc[1]); break;
+    case 3: r = dv2dy(sv.n, sv.c, sv.s, DivT{4.0 * sc[0]}, sc[1]); break;         // dely
+    case 4: r = laplacian(su.c, su.n, su.s, su.w, su.e, DivT{sc[0] * sc[0]}, DivT{sc[1] * sc[1]});
+        break;                                                                    // delx, dely
+    case 5: r = residual(su.c, su.n, su.s, su.w, su.e, DivT{sc[0] * sc[0]}, DivT{sc[1] * sc[1]},
+                         sc[2]); break;
+    case 6: r = calculate_f(su, sv, fg_div_plain<DivT>(sc[0], sc[1], sc[4]), sc[2], sc[3]); break;
+    case 7: r = calculate_g(su, sv, fg_div_plain<DivT>(sc[0], sc[1], sc[4]), sc[2], sc[3]); break;
     }
     out[0] = r;
 }
@@ -555,31 +676,58 @@ sb_status launch_velocity_bc(sb_sim *s) {
     return SB_OK;
 }
 
-sb_status launch_fg(sb_sim *s) {
-    int64_t row0 = s->halo ? s->g.own0 - 1 : 0, row1 = s->g.own1;
-    fg_kernel<<<row_grid(s->g, row1 - row0, s->g.NY), TPB, 0, s->stream>>>(
-        s->g, s->u, s->v, s->cflag, s->f, s->gq, row0, row1, s->prm.delx, s->prm.dely,
-        s->prm.delt, s->prm.gamma, s->prm.reynolds);
+static FgrConsts fgr_consts(const sb_sim *s) {
+    const sb_params &p = s->prm;
+    const double d[8] = {p.delx * p.delx, p.dely * p.dely, 4.0 * p.delx, 4.0 * p.dely,
+                         p.reynolds,      p.delx,          p.dely,       p.delt};
+    FgrConsts kc;
+    kc.fast = 1;
+    for (int i = 0; i < 8; i++) {
+        DivC c = make_divc(d[i]);
+        kc.d[i] = c.d;
+        kc.r[i] = c.r;
+        kc.fast &= c.fast;
+    }
+    kc.delt = p.delt;
+    kc.gamma = p.gamma;
+    return kc;
+}
+
+static sb_status rhs_halo(sb_sim *s) {
+    if (!s->slab) return SB_OK;
+    // the red-black tiles re-sweep their halo rows and need rhs there: edge rows -> the
+    // neighbours' halo rows, then a barrier before the first pass reads them.  (The
+    // neighbours left their previous solve long ago: the barriers of the velocity update.)
+    sb_status st = slab_put_rows(s, s->rhs, s->lo_rhs, s->hi_rhs, 8);
+    if (st) return st;
+    return slab_allreduce(s, s->d_scalars, 0, 0);
+}
+
+// what = 1: F, G (sb_calculate_f_and_g); 3: F, G and RHS in one pass (the tick)
+sb_status launch_fg_rhs(sb_sim *s, int what) {
+    const bool with_rhs = (what & 2) != 0;
+    // slab mode without the fused rhs: F of the halo row in front is stored for rhs_kernel
+    int64_t row0 = (s->halo && !with_rhs) ? s->g.own0 - 1 : s->g.own0, row1 = s->g.own1;
+    dim3 grid((unsigned)((row1 - row0 + FGR_ROWS - 1) / FGR_ROWS),
+              (unsigned)((s->g.NY + FGR_COLS - 1) / FGR_COLS));
+    fg_rhs_kernel<<<grid, 32 * FGR_WARPS, 0, s->stream>>>(
+        s->g, s->u, s->v, s->cflag, s->f, s->gq, s->rhs, row0, row1, s->g.own0, fgr_consts(s), 1,
+        with_rhs ? 1 : 0);
     s->launches++;
     SB_CUDA(cudaGetLastError());
-    return SB_OK;
+    return with_rhs ? rhs_halo(s) : SB_OK;
 }
+
+sb_status launch_fg(sb_sim *s) { return launch_fg_rhs(s, 1); }
 
 sb_status launch_rhs(sb_sim *s) {
     int64_t row0 = s->g.own0, row1 = s->g.own1;
     rhs_kernel<<<row_grid(s->g, row1 - row0, s->g.NY), TPB, 0, s->stream>>>(
-        s->g, s->f, s->gq, s->rhs, row0, row1, s->prm.delx, s->prm.dely, s->prm.delt);
+        s->g, s->f, s->gq, s->rhs, row0, row1, make_divc(s->prm.delx), make_divc(s->prm.dely),
+        make_divc(s->prm.delt));
     s->launches++;
     SB_CUDA(cudaGetLastError());
-    if (s->slab) {
-        // the red-black tiles re-sweep their halo rows and need rhs there: edge rows -> the
-        // neighbours' halo rows, then a barrier before the first pass reads them.  (The
-        // neighbours left their previous solve long ago: the barriers of the velocity update.)
-        sb_status st = slab_put_rows(s, s->rhs, s->lo_rhs, s->hi_rhs, 8);
-        if (st) return st;
-        return slab_allreduce(s, s->d_scalars, 0, 0);
-    }
-    return SB_OK;
+    return rhs_halo(s);
 }
 
 sb_status launch_pressure_bc(sb_sim *s, int guarded) {
@@ -599,7 +747,8 @@ sb_status launch_norm_partials(sb_sim *s, int guarded, int *nblocks) {
     sb_status st = ensure_partial(s, (size_t)gx * gy * 4 + 64);
     if (st) return st;
     norm_partial_kernel<<<dim3(gy, gx), TPB, 0, s->stream>>>(
-        s->g, pbuf_ptr(s), s->d_ctl, guarded, s->rhs, s->d_partial, s->prm.delx, s->prm.dely);
+        s->g, pbuf_ptr(s), s->d_ctl, guarded, s->rhs, s->d_partial,
+        make_divc(s->prm.delx * s->prm.delx), make_divc(s->prm.dely * s->prm.dely));
     s->launches++;
     SB_CUDA(cudaGetLastError());
     *nblocks = (int)(gx * gy);
@@ -738,7 +887,7 @@ void preload_stages() {
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, velocity_bc_gather);
     cudaFuncGetAttributes(&a, velocity_bc_scatter);
-    cudaFuncGetAttributes(&a, fg_kernel);
+    cudaFuncGetAttributes(&a, fg_rhs_kernel);
     cudaFuncGetAttributes(&a, rhs_kernel);
     cudaFuncGetAttributes(&a, pressure_bc_kernel);
     cudaFuncGetAttributes(&a, norm_partial_kernel);
