@@ -245,3 +245,17 @@ def test_nast2d_fixture(fixtures, snapshots):
     # (the snapshot holds the reference parser's 1-ulp-low pressure literal)
     assert np.array_equal(sim.kind, refjson.cells_from_json(snap["cell_type"])[0])
     assert_bits_equal(sim.u, refjson.array_from_json(snap["u"]), "u")
+
+
+# ---- the constant-divisor division of the strict kernels equals IEEE `/` -----------------
+def test_fastdiv_equals_ieee_division(tmp_path):
+    """oracle/fastdiv_check.c: Markstein correction steps vs `/` over ~6 M quotients
+    (the divisors of every BASELINE config + random ones, adversarial dividends)."""
+    import subprocess
+    from pathlib import Path
+    src = Path(__file__).resolve().parent.parent / "oracle" / "fastdiv_check.c"
+    exe = tmp_path / "fastdiv_check"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), str(src), "-lm"], check=True)
+    r = subprocess.run([str(exe), "4000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    assert " 0 mismatches" in r.stdout
