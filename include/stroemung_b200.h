@@ -82,7 +82,7 @@ typedef struct {
     double initial_norm_squared;
     /* ---- extensions (0 = reference behaviour / defaults) ---- */
     double tau;                   /* > 0: adaptive delt (NaSt2D COMP_delt)       */
-    int32_t temporal_block;       /* red-black sweeps fused per pass, 1..4; 0 = default */
+    int32_t temporal_block;       /* red-black sweeps fused per pass, 1..4; 0 = default (3) */
     int32_t device;               /* CUDA device ordinal; -1 = current device    */
     /* row-slab decomposition along x: this handle owns global rows
      * [x_begin, x_end) of the nx rows; 0,0 = whole grid.  Host arrays passed to
@@ -237,6 +237,9 @@ uint64_t sb_kernel_launches(const sb_sim *sim);
 /* device time (ms) of the SOR solve inside the last sb_tick / sb_solve_sor / sb_sor_sweeps,
  * measured with CUDA events on the handle's stream */
 double sb_last_sor_ms(const sb_sim *sim);
+/* how the last red-black pass split the grid: tiles on the tile kernel (walls, obstacles,
+ * grid ring, slab edges) and work items of the streaming kernel (all-fluid regions) */
+sb_status sb_rb_plan(const sb_sim *sim, int32_t *tile_kernel_tiles, int32_t *stream_items);
 /* per-pass profiling of the dominant kernel: when enabled, every SOR sweep-kernel launch
  * (red-black pass or wavefront sweep) is bracketed by CUDA events on the handle's stream.
  * sb_profile_read returns the durations (ms) recorded since the last read, oldest first;

@@ -60,6 +60,7 @@ static void destroy(sb_sim *s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     slab_release(s);
+    rb_plan_release(s);
     cudaFree(s->d_hist);
     cudaFree(s->p[0]); cudaFree(s->p[1]); cudaFree(s->u); cudaFree(s->v); cudaFree(s->f);
     cudaFree(s->gq); cudaFree(s->rhs); cudaFree(s->cflag);
@@ -91,7 +92,7 @@ static sb_status allocate(const sb_params *params, sb_sim **out) {
     sb_sim *s = new (std::nothrow) sb_sim();
     if (!s) return SB_INVALID_ARGUMENT;
     s->prm = *params;
-    if (s->prm.temporal_block == 0) s->prm.temporal_block = 2;
+    if (s->prm.temporal_block == 0) s->prm.temporal_block = 3;
     if (params->device >= 0) s->device = params->device;
     else cudaGetDevice(&s->device);
     cudaError_t e = cudaSetDevice(s->device);
@@ -669,7 +670,7 @@ sb_status sb_set_params(sb_sim *sim, const sb_params *p) {
     sim->prm.sor_absolute_epsilon = p->sor_absolute_epsilon; sim->prm.omega = p->omega;
     sim->prm.max_iterations = p->max_iterations; sim->prm.tau = p->tau;
     sim->prm.sor_mode = p->sor_mode;
-    sim->prm.temporal_block = p->temporal_block ? p->temporal_block : 2;
+    sim->prm.temporal_block = p->temporal_block ? p->temporal_block : 3;
     sim->time = p->time;
     sim->iterations = p->iterations;
     sim->has_initial_norm = p->has_initial_norm;
@@ -850,6 +851,12 @@ sb_status sb_timer_end(sb_sim *sim, double *elapsed_ms) {
     return SB_OK;
 }
 
+sb_status sb_rb_plan(const sb_sim *sim, int32_t *tile_kernel_tiles, int32_t *stream_items) {
+    if (!sim || !tile_kernel_tiles || !stream_items) return SB_INVALID_ARGUMENT;
+    *tile_kernel_tiles = sim->plan.n_slow;
+    *stream_items = sim->plan.n_items;
+    return SB_OK;
+}
 uint64_t sb_kernel_launches(const sb_sim *sim) { return sim ? sim->launches : 0; }
 double sb_last_sor_ms(const sb_sim *sim) { return sim ? sim->last_sor_ms : 0.0; }
 void *sb_stream(const sb_sim *sim) { return sim ? (void *)sim->stream : nullptr; }

@@ -247,6 +247,7 @@ sb_status alloc_list(cudaStream_t st, BList &b, uint64_t n) {
 // BTreeSet, and get rewritten by the caller's rollback + re-classification.
 sb_status classify(sb_sim *s) {
     const Geom &g = s->g;
+    s->flag_epoch++;
     int64_t total = g.nxl * g.NY;
     unsigned long long init[2] = {~0ull, 0ull};
     SB_CUDA(cudaMemcpyAsync(s->d_err, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));

@@ -149,6 +149,7 @@ dim3 cell_grid(const Geom &g) { return dim3((unsigned)g.nxl, (unsigned)((g.pitch
 }  // namespace
 
 sb_status launch_mark_valid(sb_sim *s, const uint8_t *d_kind_rows, int keep_edges) {
+    s->flag_epoch++;
     mark_valid_kernel<<<cell_grid(s->g), 256, 0, s->stream>>>(s->g, s->cflag, d_kind_rows,
                                                               keep_edges);
     s->launches++;
@@ -157,6 +158,7 @@ sb_status launch_mark_valid(sb_sim *s, const uint8_t *d_kind_rows, int keep_edge
 }
 
 sb_status restore_edges_from_list(sb_sim *s) {
+    s->flag_epoch++;
     clear_edges_kernel<<<cell_grid(s->g), 256, 0, s->stream>>>(s->g, s->cflag);
     s->launches++;
     if (s->bl.n) {
@@ -168,6 +170,7 @@ sb_status restore_edges_from_list(sb_sim *s) {
 }
 
 sb_status launch_preset(sb_sim *s, int preset, const double *args) {
+    s->flag_epoch++;
     PresetArgs pa;
     pa.preset = preset;
     pa.a0 = (int64_t)args[0];
@@ -181,6 +184,7 @@ sb_status launch_preset(sb_sim *s, int preset, const double *args) {
 
 sb_status launch_edit_block(sb_sim *s, int64_t gx, int64_t gy, uint8_t kind, double *backup,
                             int restore, int32_t *modified) {
+    s->flag_epoch++;
     edit_block_kernel<<<1, 32, 0, s->stream>>>(s->g, s->cflag, s->u, s->v, s->p[s->cur], gx, gy,
                                                kind, backup, restore, modified);
     s->launches++;

@@ -93,6 +93,27 @@ struct SlabLink {
     int64_t lo_row0, hi_row0;
 };
 
+// ---- red-black pass: which parts of the grid take the streaming kernel (sor_rb_stream.cu) --
+// one work item of the streaming kernel: local rows [x0, x1) of the 128-column strip whose
+// first column (halo included) is ty0
+struct RbItem {
+    int32_t x0, x1, ty0, pad;
+};
+// The lattice of the tile kernel (BX x BY inner regions) split into "slow" tiles -- anything
+// with a wall, an obstacle, the grid ring or a slab edge in its footprint; they keep the tile
+// kernel -- and runs of "plain" tiles (all-fluid footprint) along x that one warp streams
+// through.  Rebuilt when the cell flags or the temporal block change.
+struct RbPlan {
+    uint64_t epoch = 0;      // sb_sim::flag_epoch it was built for (0 = never)
+    int T = 0;               // temporal block it was built for
+    int tiles_x = 0, tiles_y = 0;
+    int n_slow = 0, n_items = 0;
+    int32_t *d_slow = nullptr;   // tile ids of the slow tiles
+    RbItem *d_items = nullptr;
+    uint8_t *d_plain = nullptr;  // scratch: one byte per tile
+    size_t cap_tiles = 0, cap_items = 0;
+};
+
 #define SB_CUDA(call)                                                               \
     do {                                                                            \
         cudaError_t _e = (call);                                                    \
@@ -120,6 +141,8 @@ struct sb_sim {
     int cur = 0;
     double *u = nullptr, *v = nullptr, *f = nullptr, *gq = nullptr, *rhs = nullptr;
     uint8_t *cflag = nullptr;
+    uint64_t flag_epoch = 1;      // bumped by everything that writes cflag
+    sb::RbPlan plan;
     size_t field_bytes = 0, flag_bytes = 0;
     sb::BList bl;
     // sparse velocity table as given by the host (global coordinates)
@@ -197,6 +220,11 @@ sb_status launch_sor_lex_sweep(sb_sim *s, int guarded);
 // sor_rb.cu
 sb_status launch_sor_rb_pass(sb_sim *s, int *ntiles, int norm_only);
 int rb_halo_rows(int T);
+// sor_rb_stream.cu
+sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h);
+sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h);
+void rb_plan_release(sb_sim *s);
+void preload_sor_rb_stream();
 // profiling hooks (capi.cu): record an event of the current pass on the stream
 void prof_mark(sb_sim *s);
 // finalize (stages.cu): sum partials, exit test, update ctl

@@ -141,8 +141,10 @@ sb_status slab_sync_halos(sb_sim *s, int with_flags) {
     if ((st = slab_put_rows(s, s->p[c], s->link.lo_p[c], s->link.hi_p[c], 8))) return st;
     if ((st = slab_put_rows(s, s->u, s->lo_u, s->hi_u, 8))) return st;
     if ((st = slab_put_rows(s, s->v, s->lo_v, s->hi_v, 8))) return st;
-    if (with_flags)
+    if (with_flags) {
+        s->flag_epoch++;  // the neighbours rewrite my halo rows' flags as well
         if ((st = slab_put_rows(s, s->cflag, s->lo_flag, s->hi_flag, 1))) return st;
+    }
     return slab_allreduce(s, s->d_scalars, 0, 0);
 }
 
@@ -174,6 +176,7 @@ sb_status slab_prepare(sb_sim *s) {
     preload_grid();
     preload_stages();
     preload_sor_rb();
+    preload_sor_rb_stream();
     s->slab = true;
     s->connected = false;
     memset(&s->link, 0, sizeof(s->link));

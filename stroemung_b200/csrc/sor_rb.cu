@@ -44,14 +44,16 @@
 //     t     = fma(1/dx^2, pE+pW, fma(1/dy^2, pS+pN, -rhs))
 //     p_new = fma(mid, t, (1-w)*p)            mid = w / (2/dx^2 + 2/dy^2)
 //     r     = fma(-(2/dx^2 + 2/dy^2), p, t)   residual, all interior cells
-#include "sb_internal.cuh"
+#include <stdlib.h>
+
+#include "sor_rb.cuh"
 
 namespace sb {
 
 namespace {
 
-constexpr int TXR = 48;                 // tile rows
-constexpr int TW = 128;                 // tile columns
+constexpr int TXR = RB_TXR;             // tile rows
+constexpr int TW = RB_TW;               // tile columns
 #ifndef SB_RB_NTHR
 #define SB_RB_NTHR 256
 #endif
@@ -59,17 +61,13 @@ constexpr int NTHR = SB_RB_NTHR;
 constexpr int TCOLS = TW / 2;           // thread columns (2 cells each)
 constexpr int TROWS = NTHR / TCOLS;     // thread rows
 constexpr int RPT = TXR / TROWS;        // rows per thread
-constexpr int TMAX = 4;
+constexpr int TMAX = RB_TMAX;
 constexpr int TILE = TXR * TW;
 constexpr int NWARP = NTHR / 32;
 constexpr int SMEM_PAD = 128;  // in front of the p tile: the ring cells' out-of-tile reads
 constexpr size_t SMEM_BYTES = SMEM_PAD + (size_t)TILE * 17 + 64 + NWARP * TMAX * sizeof(double);
 static_assert(TXR % TROWS == 0 && RPT % 2 == 0, "rows must split evenly, even per thread");
 static_assert(2 * RPT <= 32, "cell masks are 32-bit");
-
-struct RbConsts {
-    double rdx2, rdy2, diag, mid, omw;
-};
 
 // row-slab mode: the neighbours' pressure buffers (nullptr at the chain ends / single GPU)
 // and the row of THEIR array that receives my first (lo) / last (hi) H owned rows
@@ -78,41 +76,6 @@ struct RbPeers {
     int64_t lo_row0, hi_row0;
     int H;
 };
-
-// ---- mbarrier / TMA wrappers (inline PTX) -------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1,
-                                            uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
-        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
 
 __device__ __forceinline__ double2 lds2(const double *sp, int idx) {
     return *reinterpret_cast<const double2 *>(sp + idx);
@@ -345,8 +308,8 @@ __global__ void __launch_bounds__(NTHR, 2)
 sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__ CUtensorMap tm_p1,
               const __grid_constant__ CUtensorMap tm_rhs, const uint8_t *__restrict__ cflag,
               Geom g, double *const *__restrict__ pbuf, const SorCtl *__restrict__ ctl,
-              double *__restrict__ partial, int tiles_y, int ntiles, int h, RbConsts k,
-              int norm_only, RbPeers peers) {
+              double *__restrict__ partial, int tiles_y, int part_stride, int h, RbConsts k,
+              int norm_only, RbPeers peers, const int32_t *__restrict__ tile_list) {
     // norm_only: no sweeps, no write-back; partial[tile] = sum of squared residuals of the
     // current field (calculate_norm_squared on its own, src/simulation.rs:216-227)
     const int T = norm_only ? 0 : ctl->active_T;
@@ -361,7 +324,9 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
     double *sred = reinterpret_cast<double *>(sf + TILE + 64);  // [TMAX][NWARP]
 
     const int BX = TXR - 2 * h, BY = TW - 2 * h;  // h is even: owned columns 16-byte aligned
-    const int tile_i = blockIdx.x / tiles_y, tile_j = blockIdx.x - tile_i * tiles_y;
+    // tile_list: the tiles this launch covers (nullptr = all of the lattice)
+    const int tile = tile_list ? tile_list[blockIdx.x] : (int)blockIdx.x;
+    const int tile_i = tile / tiles_y, tile_j = tile - tile_i * tiles_y;
     const int tx0 = (SLAB ? (int)g.own0 : 0) + tile_i * BX - h;  // local row of tile row 0 (even)
     const int ty0 = tile_j * BY - h;   // column of tile column 0 (even)
 
@@ -604,7 +569,7 @@ sor_rb_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__
     if ((int)threadIdx.x < levels) {
         double tsum = 0.0;
         for (int w = 0; w < NWARP; w++) tsum += sred[threadIdx.x * NWARP + w];
-        partial[(int64_t)threadIdx.x * ntiles + blockIdx.x] = tsum;
+        partial[(int64_t)threadIdx.x * part_stride + blockIdx.x] = tsum;
     }
 }
 
@@ -660,13 +625,20 @@ sb_status ensure_tmaps(sb_sim *s) {
 
 int rb_halo_rows(int T) { return 2 * T + 2; }
 
-static double *const *pbuf_ptr(sb_sim *s) {
-    return reinterpret_cast<double *const *>(reinterpret_cast<char *>(s->d_ctl) + 256);
+// SB_RB_STREAM=0 keeps every tile on the tile kernel (A/B measurements)
+static bool rb_stream_enabled() {
+    static int env = -1;
+    if (env < 0) {
+        const char *e = getenv("SB_RB_STREAM");
+        env = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return env != 0;
 }
 
 // one guarded pass: performs ctl->active_T sweeps from pbuf[ctl->src] into the other buffer
-// (norm_only: just the residual partial sums of pbuf[ctl->src])
-sb_status launch_sor_rb_pass(sb_sim *s, int *ntiles_out, int norm_only) {
+// (norm_only: just the residual partial sums of pbuf[ctl->src]).  The all-fluid part of the
+// grid goes to the streaming kernel (sor_rb_stream.cu), everything else to the tile kernel.
+sb_status launch_sor_rb_pass(sb_sim *s, int *nparts_out, int norm_only) {
     sb_status st = ensure_tmaps(s);
     if (st) return st;
     const Geom &g = s->g;
@@ -675,7 +647,16 @@ sb_status launch_sor_rb_pass(sb_sim *s, int *ntiles_out, int norm_only) {
     int BX = TXR - 2 * h, BY = TW - 2 * h;
     int tiles_x = (int)((g.own1 - g.own0 + BX - 1) / BX), tiles_y = (int)((g.NY + BY - 1) / BY);
     int ntiles = tiles_x * tiles_y;
-    size_t need = (size_t)ntiles * TMAX + 64;
+    int n_tile = ntiles, n_items = 0;
+    const int32_t *tile_list = nullptr;
+    if (!norm_only && rb_stream_enabled()) {
+        if ((st = rb_ensure_plan(s, BX, BY, h))) return st;
+        n_tile = s->plan.n_slow;
+        n_items = s->plan.n_items;
+        tile_list = s->plan.d_slow;
+    }
+    const int nparts = n_tile + n_items;
+    size_t need = (size_t)nparts * TMAX + 64;
     if (need > s->partial_cap) {  // stream-ordered: no device-wide synchronisation
         if (s->d_partial) SB_CUDA(cudaFreeAsync(s->d_partial, s->stream));
         s->d_partial = nullptr;
@@ -688,26 +669,26 @@ sb_status launch_sor_rb_pass(sb_sim *s, int *ntiles_out, int norm_only) {
     peers.hi_p[0] = s->link.hi_p[0]; peers.hi_p[1] = s->link.hi_p[1];
     peers.lo_row0 = s->link.lo_row0; peers.hi_row0 = s->link.hi_row0;
     peers.H = s->link.H;
-    RbConsts k;
-    double dx2 = s->prm.delx * s->prm.delx, dy2 = s->prm.dely * s->prm.dely;
-    k.rdx2 = 1.0 / dx2;
-    k.rdy2 = 1.0 / dy2;
-    k.diag = (2.0 * k.rdx2) + (2.0 * k.rdy2);
-    k.mid = s->prm.omega / ((2.0 / dx2) + (2.0 / dy2));
-    k.omw = 1.0 - s->prm.omega;
+    const RbConsts k = rb_consts(s);
     // tile row 0 is local row -h (even offset): the colour of the thread's first row follows
     // the parity of the slab's global row offset
     const int par = (int)(((g.gx0 % 2) + 2) % 2);
     if (!norm_only) prof_mark(s);
-    auto kern = s->slab ? (par ? sor_rb_kernel<1, true> : sor_rb_kernel<0, true>)
-                        : (par ? sor_rb_kernel<1, false> : sor_rb_kernel<0, false>);
-    kern<<<ntiles, NTHR, SMEM_BYTES, s->stream>>>(s->tm_p[0], s->tm_p[1], s->tm_rhs, s->cflag, g,
-                                                  pbuf_ptr(s), s->d_ctl, s->d_partial, tiles_y,
-                                                  ntiles, h, k, norm_only, peers);
+    if (n_tile > 0) {
+        auto kern = s->slab ? (par ? sor_rb_kernel<1, true> : sor_rb_kernel<0, true>)
+                            : (par ? sor_rb_kernel<1, false> : sor_rb_kernel<0, false>);
+        kern<<<n_tile, NTHR, SMEM_BYTES, s->stream>>>(s->tm_p[0], s->tm_p[1], s->tm_rhs, s->cflag,
+                                                      g, rb_pbuf_ptr(s), s->d_ctl, s->d_partial,
+                                                      tiles_y, nparts, h, k, norm_only, peers,
+                                                      tile_list);
+        s->launches++;
+    }
+    if (n_items > 0) {
+        if ((st = launch_sor_rb_stream(s, n_tile, nparts, h))) return st;
+    }
     if (!norm_only) prof_mark(s);
-    s->launches++;
     SB_CUDA(cudaGetLastError());
-    *ntiles_out = ntiles;
+    *nparts_out = nparts;
     return SB_OK;
 }
 

@@ -335,6 +335,13 @@ class Simulation:
     def kernel_launches(self):
         return int(_capi.lib().sb_kernel_launches(self._h))
 
+    @property
+    def rb_plan(self):
+        """(tiles on the tile kernel, work items of the streaming kernel) of the last pass"""
+        a, b = C.c_int32(), C.c_int32()
+        self._check(_capi.lib().sb_rb_plan(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def timer_begin(self):
         self._check(_capi.lib().sb_timer_begin(self._h))
 

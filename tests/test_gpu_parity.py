@@ -281,6 +281,35 @@ def test_red_black_sweeps_match_oracle(shape, seed, T):
     assert close(sim.calculate_norm_squared(), o.calculate_norm_squared())
 
 
+@pytest.mark.parametrize("T", [1, 2, 3, 4])
+@pytest.mark.parametrize("shape,blocks,seed", [((200, 300), 0, 41), ((330, 420), 3, 42),
+                                               ((130, 700), 1, 43)])
+def test_red_black_streaming_regions_match_oracle(shape, blocks, seed, T):
+    """Grids large enough for all-fluid regions: those go through the streaming kernel
+    (sor_rb_stream.cu), the rest through the tile kernel; together bit-exact vs the oracle,
+    including the shortened last pass (7 sweeps) and the norm of every sweep."""
+    nx, ny = shape
+    kind, bu, bv = random_mask(nx, ny, seed, n_blocks=blocks)
+    p, u, v = random_fields(nx, ny, seed)
+    unf = unfinalized(nx, ny, kind, bu, bv, p=p, u=u, v=v)
+    sim = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK, temporal_block=T)
+    o = oracle_from(unf, sor_mode=po.SOR_RED_BLACK)
+    n = 7
+    norms = sim.sor_sweeps(n)
+    slow, items = sim.rb_plan
+    assert slow > 0 and (items > 0 or blocks > 1), (slow, items)
+    for k in range(n):
+        o.sor_sweep()
+        assert close(norms[k], o.calculate_norm_squared()), (k, norms[k])
+    assert_bits_equal(sim.grid.pressure, o.p, "p after red-black sweeps")
+    for t in range(2):   # full ticks on top (exit test, redo passes, velocity update)
+        it, nrm = sim.run_simulation_tick()
+        oit, onrm = o.run_simulation_tick()
+        assert it == oit and close(nrm, onrm), (t, it, oit, nrm, onrm)
+    assert_bits_equal(sim.grid.pressure, o.p, "p after ticks")
+    assert_bits_equal(sim.grid.u, o.u, "u after ticks")
+
+
 @pytest.mark.parametrize("T", [1, 2, 4])
 def test_red_black_ticks_match_oracle(T):
     shape = (100, 20)
