@@ -69,6 +69,9 @@ typedef enum {
     SB_FIELD_EDGE = 7                                   /* boundary edge class (u8, read-only) */
 } sb_field;
 
+/* ColorType (src/visualization.rs:72-77) */
+typedef enum { SB_COLOR_PRESSURE = 0, SB_COLOR_SPEED = 1 } sb_color_type;
+
 /* UnfinalizedSimulation (src/simulation.rs:30-44) minus the arrays, plus extensions.
  * Zero-initialise, then fill. */
 typedef struct {
@@ -184,6 +187,14 @@ sb_status sb_edit_cells(sb_sim *sim, uint64_t x, uint64_t y, uint8_t kind, doubl
  * 5 lid-driven cavity (args: lid_u) */
 sb_status sb_create_preset(const sb_params *params, int32_t preset, const double *args,
                            size_t n_args, sb_sim **out);
+
+/* render_simulation (src/visualization.rs:79-105) with color_pressure / color_speed /
+ * hsl_to_rgb (:7-70) evaluated on the device from the resident fields and the current
+ * pressure_range / speed_range: writes the RGBA8 frame in macroquad's Image layout (row-major,
+ * width = nx, pixel (x, y) at byte 4 (y nx + x)) to host memory -- 4 bytes per cell over
+ * PCIe instead of downloading p / u / v and the cell types.  A slab handle renders its
+ * owned rows: an image of width x_end - x_begin. */
+sb_status sb_render_rgba(sb_sim *sim, int32_t color_type, uint8_t *dst);
 
 /* ---- errors -------------------------------------------------------------------- */
 /* cell named by the last SB_BOUNDARY_TOO_THIN (global x, y) and its kind;

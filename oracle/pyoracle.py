@@ -89,6 +89,8 @@ def lib():
         getattr(L, name).restype = dp
     L.so_kind.argtypes = [vp]
     L.so_kind.restype = u8p
+    L.so_render_rgba.argtypes = [vp, C.c_int, u8p]
+    L.so_render_rgba.restype = None
     L.so_get_state.argtypes = [vp, C.POINTER(State)]
     L.so_get_state.restype = None
     L.so_set_params.argtypes = [vp, C.POINTER(Params)]
@@ -310,6 +312,12 @@ class OracleSim:
 
     def calculate_speed_range(self):
         lib().so_calculate_speed_range(self._h)
+
+    def render_simulation(self, color_type="pressure"):
+        """render_simulation (src/visualization.rs:79-105): (ny, nx, 4) uint8"""
+        img = np.empty((self.ny, self.nx, 4), dtype=np.uint8)
+        lib().so_render_rgba(self._h, {"pressure": 0, "speed": 1}[color_type], _u8p(img))
+        return img
 
     def run_simulation_tick(self):
         it = C.c_uint32()

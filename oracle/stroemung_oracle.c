@@ -236,6 +236,67 @@ void so_calculate_speed_range(so_sim *s) {
 }
 
 /* ------------------------------------------------------------------ */
+/* colour mapping: src/visualization.rs (N4)                           */
+/* ------------------------------------------------------------------ */
+/* Rust `as u8` on an f32: saturating, NaN -> 0 */
+static uint8_t sat_u8(float v) {
+    if (!(v > 0.0f)) return 0;
+    if (v >= 255.0f) return 255;
+    return (uint8_t)v;
+}
+
+/* hsl_to_rgb (src/visualization.rs:7-27), all f32; `%` on floats is fmodf.  The result goes
+ * through macroquad 0.4.13's `From<Color> for [u8; 4]` = `(c * 255.) as u8` per channel
+ * (crate not vendored: Cargo.lock:284-285; Image::set_pixel stores that at y*width + x). */
+static void hsl_to_rgba8(float hue, float saturation, float lightness, uint8_t out[4]) {
+    const float c = (1.0f - fabsf(2.0f * lightness - 1.0f)) * saturation;
+    const float q = hue / 60.0f;
+    const float x = c * (1.0f - fabsf(fmodf(q, 2.0f) - 1.0f));
+    const float m = lightness - c / 2.0f;
+    float r, g, b;
+    if (hue < 60.0f) { r = c; g = x; b = 0.0f; }
+    else if (hue < 120.0f) { r = x; g = c; b = 0.0f; }
+    else if (hue < 180.0f) { r = 0.0f; g = c; b = x; }
+    else if (hue < 240.0f) { r = 0.0f; g = x; b = c; }
+    else if (hue < 300.0f) { r = x; g = 0.0f; b = c; }
+    else { r = c; g = 0.0f; b = x; }
+    const float rr = r + m, gg = g + m, bb = b + m;
+    out[0] = sat_u8(rr * 255.0f);
+    out[1] = sat_u8(gg * 255.0f);
+    out[2] = sat_u8(bb * 255.0f);
+    out[3] = sat_u8(1.0f * 255.0f);
+}
+
+/* render_simulation (src/visualization.rs:79-105) with color_pressure (:49-70) and
+ * color_speed (:29-47); color_type 0 = Pressure, 1 = Speed (ColorType, :72-77).
+ * rgba: ny rows of nx pixels (macroquad Image layout). */
+void so_render_rgba(const so_sim *s, int color_type, uint8_t *rgba) {
+    for (uint64_t x = 0; x < s->nx; x++) {
+        for (uint64_t y = 0; y < s->ny; y++) {
+            uint64_t i = IDX(s, x, y);
+            uint8_t *px = rgba + 4 * (y * s->nx + x);
+            if (s->kind[i] != SO_KIND_FLUID) {
+                /* Color::new(0.5, 0.0, 0.0, 1.0) / (0.5, 0.5, 0.5, 1.0) */
+                px[0] = sat_u8(0.5f * 255.0f);
+                px[1] = px[2] = color_type ? sat_u8(0.5f * 255.0f) : 0;
+                px[3] = 255;
+                continue;
+            }
+            double q, lo, hi;
+            if (color_type) {
+                q = sqrt((s->u[i] * s->u[i]) + (s->v[i] * s->v[i]));
+                lo = s->speed_range[0]; hi = s->speed_range[1];
+            } else {
+                q = s->p[i];
+                lo = s->pressure_range[0]; hi = s->pressure_range[1];
+            }
+            float hue = (float)(240.0 - (((q - lo) * 240.0) / (hi - lo)));
+            hsl_to_rgba8(hue, 1.0f, 0.5f, px);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ */
 /* pressure BC: src/grid/mod.rs:343-412                                */
 /* ------------------------------------------------------------------ */
 int so_copy_pressure_to_boundaries(so_sim *s) {

@@ -104,6 +104,9 @@ void so_set_u_and_v(so_sim *s);               /* src/simulation.rs:287-322 */
 void so_calculate_pressure_range(so_sim *s);  /* src/grid/mod.rs:237-251   */
 void so_calculate_speed_range(so_sim *s);     /* src/grid/mod.rs:253-268   */
 int so_tick(so_sim *s, uint32_t *iters, double *norm_squared); /* src/simulation.rs:324-333 */
+/* render_simulation (src/visualization.rs:79-105): RGBA8, ny rows of nx pixels;
+ * color_type 0 = Pressure, 1 = Speed */
+void so_render_rgba(const so_sim *s, int color_type, uint8_t *rgba);
 
 /* exactly one SOR iteration in the mode of the handle (BC copy + sweep), no norm */
 void so_sor_sweep(so_sim *s);

@@ -16,6 +16,7 @@ LIB_PATH = Path(os.environ.get("SB_LIB", _DIR / "libstroemung_b200.so"))
  SB_INVALID_ARGUMENT) = range(5)
 KIND_FLUID, KIND_NOSLIP, KIND_OUTFLOW, KIND_INFLOW, KIND_MOVING_WALL = range(5)
 SOR_REFERENCE_ORDER, SOR_RED_BLACK = 0, 1
+COLOR_PRESSURE, COLOR_SPEED = 0, 1  # ColorType (src/visualization.rs:72-77)
 SLAB_BLOB_BYTES = 1024
 SLAB_HALO = 10
 (FIELD_P, FIELD_U, FIELD_V, FIELD_F, FIELD_G, FIELD_RHS, FIELD_KIND, FIELD_EDGE) = range(8)
@@ -66,7 +67,7 @@ SYMBOLS = [
     "sb_calculate_pressure_range", "sb_calculate_speed_range", "sb_sor_sweeps", "sb_download",
     "sb_upload", "sb_host_alloc", "sb_host_free", "sb_get_state", "sb_set_params",
     "sb_set_boundary_velocities", "sb_rebuild_boundary_list", "sb_boundary_list",
-    "sb_edit_cells", "sb_create_preset", "sb_error_cell", "sb_last_error_string",
+    "sb_edit_cells", "sb_render_rgba", "sb_create_preset", "sb_error_cell", "sb_last_error_string",
     "sb_slab_export", "sb_slab_connect", "sb_slab_sync_halos", "sb_du2dx", "sb_duvdx", "sb_duvdy",
     "sb_dv2dy", "sb_laplacian", "sb_residual", "sb_calculate_f", "sb_calculate_g",
     "sb_profile_enable", "sb_profile_read", "sb_timer_begin", "sb_timer_end", "sb_kernel_launches", "sb_last_sor_ms", "sb_stream",
@@ -111,6 +112,7 @@ def lib():
         "sb_rebuild_boundary_list": ([vp], C.c_int),
         "sb_boundary_list": ([vp, u64p, u8p, C.c_uint64, u64p], C.c_int),
         "sb_edit_cells": ([vp, C.c_uint64, C.c_uint64, C.c_uint8, d, d, i32p], C.c_int),
+        "sb_render_rgba": ([vp, C.c_int32, vp], C.c_int),
         "sb_error_cell": ([vp, u64p, u8p], C.c_int),
         "sb_last_error_string": ([], C.c_char_p),
         "sb_slab_export": ([vp, u8p], C.c_int),

@@ -62,6 +62,7 @@ static void destroy(sb_sim *s) {
     slab_release(s);
     rb_plan_release(s);
     cudaFree(s->d_hist);
+    cudaFree(s->d_img);
     cudaFree(s->p[0]); cudaFree(s->p[1]); cudaFree(s->u); cudaFree(s->v); cudaFree(s->f);
     cudaFree(s->gq); cudaFree(s->rhs); cudaFree(s->cflag);
     cudaFree(s->bl.lin); cudaFree(s->bl.ke); cudaFree(s->bl.bu); cudaFree(s->bl.bv);
@@ -565,6 +566,23 @@ sb_status sb_calculate_pressure_range(sb_sim *sim) {
 sb_status sb_calculate_speed_range(sb_sim *sim) {
     SB_ENTER(sim);
     return launch_speed_range(sim);
+}
+
+// render_simulation (src/visualization.rs:79-105): the frame of the owned rows, RGBA8,
+// width = owned rows, height = ny, into host memory
+sb_status sb_render_rgba(sb_sim *sim, int32_t color_type, uint8_t *dst) {
+    SB_ENTER(sim);
+    if (!dst || (color_type != SB_COLOR_PRESSURE && color_type != SB_COLOR_SPEED)) {
+        set_error("sb_render_rgba: dst is NULL or unknown color_type");
+        return SB_INVALID_ARGUMENT;
+    }
+    const size_t bytes = (size_t)(sim->g.own1 - sim->g.own0) * (size_t)sim->g.NY * 4;
+    if (!sim->d_img) SB_CUDA(cudaMallocAsync(&sim->d_img, bytes, sim->stream));
+    sb_status st = launch_render(sim, color_type == SB_COLOR_SPEED, sim->d_img);
+    if (st) return st;
+    SB_CUDA(cudaMemcpyAsync(dst, sim->d_img, bytes, cudaMemcpyDeviceToHost, sim->stream));
+    SB_CUDA(cudaStreamSynchronize(sim->stream));
+    return SB_OK;
 }
 
 static double *field_ptr(sb_sim *s, sb_field f) {

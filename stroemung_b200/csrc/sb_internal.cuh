@@ -192,6 +192,7 @@ struct sb_sim {
     double *lo_rhs = nullptr, *hi_rhs = nullptr;
     double *d_hist = nullptr;                 // norm history of sb_sor_sweeps (grows only)
     size_t hist_cap = 0;
+    uchar4 *d_img = nullptr;                  // RGBA8 frame of sb_render_rgba (lazy)
     // tensor maps for the red-black pass (built lazily per buffer)
     bool tmaps_ready = false;
     CUtensorMap tm_p[2], tm_rhs, tm_flag;
@@ -252,6 +253,9 @@ void preload_classify();
 void preload_grid();
 void preload_stages();
 void preload_sor_rb();
+void preload_render();
+// render.cu: colour-map the owned rows into d_img (speed = 0: pressure, 1: speed)
+sb_status launch_render(sb_sim *s, int speed, uchar4 *d_img);
 sb_status slab_prepare(sb_sim *s);   // mailbox etc. of a world > 1 handle
 sb_status finish_create(sb_sim *s);  // capi.cu: try_from's work once the arrays are in place
 void slab_release(sb_sim *s);

@@ -177,6 +177,7 @@ sb_status slab_prepare(sb_sim *s) {
     preload_stages();
     preload_sor_rb();
     preload_sor_rb_stream();
+    preload_render();
     s->slab = true;
     s->connected = false;
     memset(&s->link, 0, sizeof(s->link));

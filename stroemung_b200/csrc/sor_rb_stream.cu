@@ -40,18 +40,35 @@ namespace sb {
 namespace {
 
 constexpr int SW = RB_TW;      // strip columns: 32 lanes x 2 pairs of columns
-constexpr int PF = 3;          // rows in flight ahead of the row being consumed
-constexpr int NP = 4;          // p ring slots  (>= PF + 1)
 constexpr int ROW_BYTES = SW * 8;
-// rhs ring slots for a temporal block of TB sweeps: a row's rhs is read until 2TB+1 ticks
-// after its arrival and is requested PF ticks before it
-__host__ __device__ constexpr int rhs_slots(int TB) { return PF + 2 * TB + 2; }
+
+// Everything that indexes a ring is a compile-time constant inside the unrolled window:
+//   * the tick loop is unrolled over NW = 2T+4 ticks (the register window), U = tick mod NW;
+//   * row R lands in slot U of the rhs ring (NW slots, one mbarrier each) and in slot
+//     U mod (T+2) of the p ring (NW/2 slots: a p row is consumed in its arrival tick);
+//   * the rhs of row q is read at ticks q+1, q+3, .. q+2T-1 (the red half-sweeps; the black
+//     cells' values are carried one tick in registers) -- the red values read at q+2T-1 are
+//     carried two more ticks for the residual of the last sweep, so a slot is free 2T ticks
+//     after its row arrived and rows can be requested PF <= 4 ticks ahead.
+__host__ __device__ constexpr int stream_nw(int T) { return 2 * T + 4; }
+__host__ __device__ constexpr int stream_np(int T) { return T + 2; }
+__host__ __device__ constexpr int stream_pf(int T) { return T == 1 ? 2 : 3; }
 __host__ __device__ constexpr int stream_smem(int TB) {
-    return (NP + rhs_slots(TB)) * ROW_BYTES + NP * 8;
+    return (stream_np(TB) + stream_nw(TB)) * ROW_BYTES + stream_nw(TB) * 8;
 }
-// warps per SM the register budget of the TB instantiation is cut for
+// warps per SM the register budget of the TB instantiation is cut for.  The register file
+// is split per SM sub-partition (16 K registers each), so the steps are 16 warps (128
+// registers per thread), 12 (168) and 8 (255): TB = 4 keeps 48 pressures per lane in flight
+// and needs the last one.
 __host__ __device__ constexpr int stream_min_ctas(int TB) {
-    return TB <= 2 ? 16 : TB == 3 ? 12 : 10;
+    return TB == 1 ? 16 : TB <= 3 ? 12 : 8;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void stg_f64x2(double *p, double a, double b) {
+    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 
 // Lane l owns column pairs A = (2l, 2l+1) and B = (64+2l, 64+2l+1) of the strip: 16-byte
@@ -62,21 +79,22 @@ struct SCtx {
     double *pout;
     int64_t pitch;
     int x0, x1;                // rows counted and stored
-    int first, nload;          // first row loaded, number of rows loaded
+    int first, re;             // rows loaded: [first, re)
     int lane, lane_m1, lane_p1;
     bool cmA, cmB;             // the pair lies in the strip's inner columns [h, SW-h)
-    double *pring, *rring;
+    double *pring, *rring;     // ring bases
+    const double *pl, *rl;     // this lane's pair A in slot 0 of the p / rhs ring
     uint64_t *bar;
     RbConsts k;
 };
 
-template <int NR>
-__device__ __forceinline__ void issue_row(const SCtx &c, int li) {
-    const int64_t off = (int64_t)(c.first + li) * c.pitch;
-    uint64_t *bar = c.bar + (li & (NP - 1));
+// request row `row` (both arrays) into rhs slot `slot` / p slot `slot % NP`; lane 0 only
+template <int NP>
+__device__ __forceinline__ void issue_row(const SCtx &c, int64_t off, int slot) {
+    uint64_t *bar = c.bar + slot;
     mbar_expect_tx(bar, 2 * ROW_BYTES);
-    bulk_load(c.pring + (li & (NP - 1)) * SW, c.pin + off, ROW_BYTES, bar);
-    bulk_load(c.rring + (li % NR) * SW, c.rhs + off, ROW_BYTES, bar);
+    bulk_load(c.pring + (slot % NP) * SW, c.pin + off, ROW_BYTES, bar);
+    bulk_load(c.rring + slot * SW, c.rhs + off, ROW_BYTES, bar);
 }
 
 // stencil sums t of the two cells of one colour in a lane's two column pairs.
@@ -104,28 +122,34 @@ __device__ __forceinline__ void stencil2(const SCtx &c, const double (&me)[4],
 }
 
 // One tick: row R has been requested PF ticks ago.  U = (R - rs) mod NW is the register slot
-// of row R; after inlining into the unrolled loop every W index below is a constant.
+// of row R and its ring slot; after inlining into the unrolled loop every index below is a
+// constant.  roff = R * pitch.  ph = parity of the mbarrier phase of this loop iteration.
 // STEADY: every row this tick touches is a counted row (no row tests at all).
-template <int T, int NR, bool STEADY>
+template <int T, bool STEADY>
 __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&C)[T][2],
-                                            double (&accA)[T], double (&accB)[T], const int U,
-                                            const int R, const SCtx &c) {
-    constexpr int NW = 2 * T + 4;
+                                            double (&FR)[2][2], double (&accA)[T],
+                                            double (&accB)[T], const int U, const int R,
+                                            const int64_t roff, const uint32_t ph,
+                                            const SCtx &c) {
+    constexpr int NW = stream_nw(T), NP = stream_np(T), PF = stream_pf(T);
     const RbConsts &k = c.k;
     const unsigned nrows = (unsigned)(c.x1 - c.x0);
-    // ---- row R: shared-memory ring -> registers; request row R + PF ------------------------
-    const int li = R - c.first;
-    if (STEADY || li >= 0) {
-        __syncwarp();  // every lane is done with the slot the next request overwrites
-        if (c.lane == 0 && li + PF < c.nload) issue_row<NR>(c, li + PF);
-        mbar_wait(c.bar + (li & (NP - 1)), (uint32_t)(li / NP) & 1u);
-        const double *src = c.pring + (li & (NP - 1)) * SW + 2 * c.lane;
+    // ---- request row R + PF; row R: shared-memory ring -> registers ------------------------
+    __syncwarp();  // every lane is done with the slots the request overwrites
+    if (c.lane == 0) {
+        if (STEADY || R + PF < c.re) issue_row<NP>(c, roff + PF * c.pitch, (U + PF) % NW);
+        if (!STEADY && R < c.first) mbar_arrive(c.bar + U);  // keeps the phases in step
+    }
+    if (STEADY || R >= c.first) {
+        mbar_wait(c.bar + U, ph);
+        const double *src = c.pl + (U % NP) * SW;
         const double2 a = *reinterpret_cast<const double2 *>(src);
         const double2 b = *reinterpret_cast<const double2 *>(src + 64);
         W[U][0] = a.x; W[U][1] = a.y; W[U][2] = b.x; W[U][3] = b.y;
     } else {
         W[U][0] = W[U][1] = W[U][2] = W[U][3] = 0.0;
     }
+    double fr_a = 0.0, fr_b = 0.0;  // red rhs of the row of the last red half-sweep
 #pragma unroll
     for (int kk = 0; kk < T; kk++) {
         // ---- red half-sweep of sweep kk on row R - (2kk+1) ---------------------------------
@@ -134,9 +158,9 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
         {
             const int lag = 2 * kk + 1;
             const int s = (U + 2 * NW - lag) % NW, sm = (s + NW - 1) % NW, sp = (s + 1) % NW;
-            const int par = (U + 2 * NW - lag) & 1;  // row parity (rs has even global x)
+            const int par = s & 1;  // row parity (rs has even global x, NW is even)
             const int q = R - lag;
-            const double *rp = c.rring + ((q - c.first + NR) % NR) * SW + 2 * c.lane;
+            const double *rp = c.rl + s * SW;
             const double2 rA = *reinterpret_cast<const double2 *>(rp);
             const double2 rB = *reinterpret_cast<const double2 *>(rp + 64);
             const bool rv = STEADY || (unsigned)(q - c.x0) < nrows;
@@ -151,6 +175,7 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
                 W[s][0] = fma(k.mid, ta, k.omw * W[s][0]);
                 W[s][2] = fma(k.mid, tb, k.omw * W[s][2]);
                 carry_a = rA.y; carry_b = rB.y;
+                if (kk == T - 1) { fr_a = rA.x; fr_b = rB.x; }
             } else {
                 stencil2<1>(c, W[s], W[sm], W[sp], rA.y, rB.y, ta, tb);
                 if (kk > 0 && rv) {
@@ -161,13 +186,14 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
                 W[s][1] = fma(k.mid, ta, k.omw * W[s][1]);
                 W[s][3] = fma(k.mid, tb, k.omw * W[s][3]);
                 carry_a = rA.x; carry_b = rB.x;
+                if (kk == T - 1) { fr_a = rA.y; fr_b = rB.y; }
             }
         }
         // ---- black half-sweep of sweep kk on row R - (2kk+2); rhs carried from last tick ---
         {
             const int lag = 2 * kk + 2;
             const int s = (U + 2 * NW - lag) % NW, sm = (s + NW - 1) % NW, sp = (s + 1) % NW;
-            const int par = (U + 2 * NW - lag) & 1;
+            const int par = s & 1;
             const int q = R - lag;
             const bool rv = STEADY || (unsigned)(q - c.x0) < nrows;
             double ta, tb;
@@ -196,29 +222,29 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
         C[kk][0] = carry_a;
         C[kk][1] = carry_b;
     }
-    // ---- residual of the red cells of the last sweep on row R - (2T+1) ---------------------
+    // ---- residual of the red cells of the last sweep on row R - (2T+1); its red rhs values
+    //      were read two ticks ago (FR[U & 1]) ------------------------------------------------
     {
         const int lag = 2 * T + 1;
         const int s = (U + 2 * NW - lag) % NW, sm = (s + NW - 1) % NW, sp = (s + 1) % NW;
-        const int par = (U + 2 * NW - lag) & 1;
+        const int par = s & 1;
         const int q = R - lag;
         if (STEADY || (unsigned)(q - c.x0) < nrows) {  // warp-uniform
-            const double *rp = c.rring + ((q - c.first + NR) % NR) * SW + 2 * c.lane;
-            const double2 rA = *reinterpret_cast<const double2 *>(rp);
-            const double2 rB = *reinterpret_cast<const double2 *>(rp + 64);
             double ta, tb;
             if (par == 0) {
-                stencil2<0>(c, W[s], W[sm], W[sp], rA.x, rB.x, ta, tb);
+                stencil2<0>(c, W[s], W[sm], W[sp], FR[U & 1][0], FR[U & 1][1], ta, tb);
                 const double ra = fma(-k.diag, W[s][0], ta), rb = fma(-k.diag, W[s][2], tb);
                 accA[T - 1] = fma(ra, ra, accA[T - 1]);
                 accB[T - 1] = fma(rb, rb, accB[T - 1]);
             } else {
-                stencil2<1>(c, W[s], W[sm], W[sp], rA.y, rB.y, ta, tb);
+                stencil2<1>(c, W[s], W[sm], W[sp], FR[U & 1][0], FR[U & 1][1], ta, tb);
                 const double ra = fma(-k.diag, W[s][1], ta), rb = fma(-k.diag, W[s][3], tb);
                 accA[T - 1] = fma(ra, ra, accA[T - 1]);
                 accB[T - 1] = fma(rb, rb, accB[T - 1]);
             }
         }
+        FR[U & 1][0] = fr_a;
+        FR[U & 1][1] = fr_b;
     }
     // ---- retire row R - (2T+2): nothing reads it any more ----------------------------------
     {
@@ -226,45 +252,60 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
         const int s = (U + 2 * NW - lag) % NW;
         const int q = R - lag;
         if (STEADY || (unsigned)(q - c.x0) < nrows) {
-            double *dst = c.pout + (int64_t)q * c.pitch + 2 * c.lane;
-            if (c.cmA) *reinterpret_cast<double2 *>(dst) = make_double2(W[s][0], W[s][1]);
-            if (c.cmB) *reinterpret_cast<double2 *>(dst + 64) = make_double2(W[s][2], W[s][3]);
+            double *dst = c.pout + (roff - lag * c.pitch);
+            if (c.cmA) stg_f64x2(dst, W[s][0], W[s][1]);
+            if (c.cmB) stg_f64x2(dst + 64, W[s][2], W[s][3]);
         }
     }
 }
 
-template <int T, int NR>
+template <int T>
 __device__ __forceinline__ void stream_item(SCtx &c, int gpar, double *__restrict__ partial,
                                             int64_t part_stride) {
-    constexpr int NW = 2 * T + 4;
+    constexpr int NW = stream_nw(T), NP = stream_np(T), PF = stream_pf(T);
     constexpr int HP = 2 * T + 2;
     c.first = c.x0 - HP;
-    const int re = c.x1 + HP;
-    c.nload = re - c.first;
+    c.re = c.x1 + HP;
     // the tick loop starts on a row of even global x so that register slot parity = row parity
     const int rs = c.first - ((gpar + c.first) & 1);
     // ticks R in [st_lo, st_hi]: all rows R-1 .. R-(2T+2) lie in [x0, x1)
     const int st_lo = c.x0 + 2 * T + 2, st_hi = c.x1;
     if (c.lane == 0) {
-#pragma unroll
-        for (int li = 0; li < PF; li++)
-            if (li < c.nload) issue_row<NR>(c, li);
+        for (int i = 0; i < NW; i++) mbar_init(c.bar + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // tick R requests row R + PF: rows below rs + PF are requested here
+        for (int r = c.first; r < rs + PF; r++)
+            if (r < c.re) issue_row<NP>(c, (int64_t)r * c.pitch, r - rs);
     }
-    double W[NW][4], C[T][2], accA[T], accB[T];
+    __syncwarp();
+    double W[NW][4], C[T][2], FR[2][2], accA[T], accB[T];
 #pragma unroll
     for (int i = 0; i < NW; i++) W[i][0] = W[i][1] = W[i][2] = W[i][3] = 0.0;
 #pragma unroll
     for (int i = 0; i < T; i++) C[i][0] = C[i][1] = accA[i] = accB[i] = 0.0;
-    for (int R0 = rs; R0 < re; R0 += NW) {
+    FR[0][0] = FR[0][1] = FR[1][0] = FR[1][1] = 0.0;
+    uint32_t ph = 0;
+    int64_t roff = (int64_t)rs * c.pitch;
+    for (int R0 = rs; R0 < c.re;) {
         if (R0 >= st_lo && R0 + NW - 1 <= st_hi) {
+            do {  // the steady state: straight-line code, no row tests
 #pragma unroll
-            for (int U = 0; U < NW; U++) stream_tick<T, NR, true>(W, C, accA, accB, U, R0 + U, c);
+                for (int U = 0; U < NW; U++) {
+                    stream_tick<T, true>(W, C, FR, accA, accB, U, R0 + U, roff, ph, c);
+                    roff += c.pitch;
+                }
+                ph ^= 1u;
+                R0 += NW;
+            } while (R0 + NW - 1 <= st_hi);
         } else {
 #pragma unroll
             for (int U = 0; U < NW; U++) {
-                if (R0 + U >= re) break;
-                stream_tick<T, NR, false>(W, C, accA, accB, U, R0 + U, c);
+                if (R0 + U >= c.re) break;
+                stream_tick<T, false>(W, C, FR, accA, accB, U, R0 + U, roff, ph, c);
+                roff += c.pitch;
             }
+            ph ^= 1u;
+            R0 += NW;
         }
     }
 #pragma unroll
@@ -275,34 +316,30 @@ __device__ __forceinline__ void stream_item(SCtx &c, int gpar, double *__restric
 }
 
 // one warp per CTA, one work item per warp; TB = the configured temporal block (the lattice
-// and the shared-memory rings follow it), the pass itself runs ctl->active_T <= TB sweeps
+// and the shared-memory budget follow it), the pass itself runs ctl->active_T <= TB sweeps
 template <int TB>
 __global__ void __launch_bounds__(32, stream_min_ctas(TB))
 sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict__ pbuf,
                      const double *__restrict__ rhs, const SorCtl *__restrict__ ctl,
                      double *__restrict__ partial, int part_base, int part_stride, int64_t pitch,
                      int gpar, int h, RbConsts k) {
-    constexpr int NR = rhs_slots(TB);
     const int T = ctl->active_T;
     if (T == 0) return;
     const int src = ctl->src;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const RbItem it = items[blockIdx.x];
     SCtx c;
-    c.pring = reinterpret_cast<double *>(smem_raw);
-    c.rring = c.pring + NP * SW;
-    c.bar = reinterpret_cast<uint64_t *>(c.rring + NR * SW);
     c.lane = threadIdx.x;
     c.lane_m1 = (c.lane + 31) & 31;
     c.lane_p1 = (c.lane + 1) & 31;
-    if (c.lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NP; i++) mbar_init(c.bar + i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
+    // rings of the T actually run: p ring, rhs ring, one mbarrier per rhs slot
+    c.pring = reinterpret_cast<double *>(smem_raw);
+    c.rring = c.pring + stream_np(T) * SW;
+    c.bar = reinterpret_cast<uint64_t *>(c.rring + stream_nw(T) * SW);
+    c.pl = c.pring + 2 * c.lane;
+    c.rl = c.rring + 2 * c.lane;
     c.pin = pbuf[src] + it.ty0;
-    c.pout = pbuf[src ^ 1] + it.ty0;
+    c.pout = pbuf[src ^ 1] + it.ty0 + 2 * c.lane;
     c.rhs = rhs + it.ty0;
     c.pitch = pitch;
     c.x0 = it.x0;
@@ -311,10 +348,10 @@ sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict
     c.cmA = 2 * c.lane >= h && 2 * c.lane < SW - h;
     c.cmB = 64 + 2 * c.lane >= h && 64 + 2 * c.lane < SW - h;
     double *part = partial + part_base + blockIdx.x;
-    if (T == TB) stream_item<TB, NR>(c, gpar, part, part_stride);
-    else if (TB > 1 && T == 1) stream_item<1, NR>(c, gpar, part, part_stride);
-    else if (TB > 2 && T == 2) stream_item<2, NR>(c, gpar, part, part_stride);
-    else if (TB > 3 && T == 3) stream_item<3, NR>(c, gpar, part, part_stride);
+    if (T == TB) stream_item<TB>(c, gpar, part, part_stride);
+    else if (TB > 1 && T == 1) stream_item<1>(c, gpar, part, part_stride);
+    else if (TB > 2 && T == 2) stream_item<2>(c, gpar, part, part_stride);
+    else if (TB > 3 && T == 3) stream_item<3>(c, gpar, part, part_stride);
 }
 
 using StreamKernel = void (*)(const RbItem *, double *const *, const double *, const SorCtl *,

@@ -336,6 +336,15 @@ class Simulation:
         return int(_capi.lib().sb_kernel_launches(self._h))
 
     @property
+    def render_simulation(self, color_type="pressure"):
+        """render_simulation (src/visualization.rs:79-105) on the device: the RGBA8 frame in
+        macroquad's Image layout, shape (ny, owned rows, 4) -- image[y, x] is the pixel of
+        cell (x, y).  color_type: "pressure" | "speed" (ColorType, :72-77)."""
+        ct = {"pressure": _capi.COLOR_PRESSURE, "speed": _capi.COLOR_SPEED}[color_type]
+        img = np.empty((self.size[1], self._local_shape[0], 4), dtype=np.uint8)
+        self._check(_capi.lib().sb_render_rgba(self._h, ct, img.ctypes.data))
+        return img
+
     def rb_plan(self):
         """(tiles on the tile kernel, work items of the streaming kernel) of the last pass"""
         a, b = C.c_int32(), C.c_int32()

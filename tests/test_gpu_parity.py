@@ -460,3 +460,40 @@ def test_draw_cells_and_rollback():
         assert sim.run_simulation_tick()[0] == o.run_simulation_tick()[0]
     assert_bits_equal(sim.grid.u, o.u, "u after edit")
     assert_bits_equal(sim.grid.pressure, o.p, "p after edit")
+
+
+# ---- N4: colour mapping (src/visualization.rs) -- oracle-only parity (the reference has no
+#      test for it), bit-exact RGBA8 --------------------------------------------------------
+@pytest.mark.parametrize("shape,seed", [((34, 18), 51), ((100, 20), 52), ((257, 129), 53)])
+def test_render_matches_oracle(shape, seed):
+    nx, ny = shape
+    kind, bu, bv = random_mask(nx, ny, seed)
+    p, u, v = random_fields(nx, ny, seed)
+    unf = unfinalized(nx, ny, kind, bu, bv, p=p, u=u, v=v)
+    sim = Simulation.try_from(unf)
+    o = oracle_from(unf)
+    for tick in range(3):
+        for ct in ("pressure", "speed"):
+            a, b = sim.render_simulation(ct), o.render_simulation(ct)
+            assert a.shape == (ny, nx, 4)
+            assert np.array_equal(a, b), (ct, tick, np.argwhere(a != b)[:4])
+        sim.run_simulation_tick()
+        o.run_simulation_tick()
+    # pressures outside a stale range (the range is only refreshed when SOR hits its cap):
+    # hues below 0 and above 240 go through the same saturating casts
+    sim.grid.pressure = p * 7.0
+    o.p[:] = p * 7.0
+    assert np.array_equal(sim.render_simulation("pressure"), o.render_simulation("pressure"))
+    sim.close()
+
+
+def test_render_degenerate_range():
+    """fields at rest: range (0, 0) -> 0/0 = NaN hue -> `as u8` gives 0 (Rust saturating cast)"""
+    nx, ny = 64, 32
+    kind, bu, bv = po.preset("obstacle", nx, ny)
+    unf = unfinalized(nx, ny, kind, bu, bv)
+    sim = Simulation.try_from(unf)
+    o = oracle_from(unf)
+    for ct in ("pressure", "speed"):
+        assert np.array_equal(sim.render_simulation(ct), o.render_simulation(ct))
+    sim.close()

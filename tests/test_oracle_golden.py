@@ -259,3 +259,46 @@ def test_fastdiv_equals_ieee_division(tmp_path):
     r = subprocess.run([str(exe), "4000"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout
     assert " 0 mismatches" in r.stdout
+
+
+# ---- N4 colour mapping: no golden data in the reference (parity unpinned); the C
+#      restatement is cross-checked against an independent numpy-f32 restatement ----------
+def _hsl_numpy(hue):
+    f = np.float32
+    hue = hue.astype(f)
+    with np.errstate(invalid="ignore"):
+        x = f(1.0) - np.abs(np.fmod(hue / f(60.0), f(2.0)) - f(1.0))
+    z, c = np.zeros_like(hue), np.ones_like(hue)
+    conds = [hue < 60, hue < 120, hue < 180, hue < 240, hue < 300]
+    r = np.select(conds, [c, x, z, z, x], c)
+    g = np.select(conds, [x, c, c, x, z], z)
+    b = np.select(conds, [z, z, x, c, c], x)
+
+    def u8(ch):
+        v = ch * f(255.0)
+        return np.where(np.isnan(v) | (v <= 0), 0, np.minimum(v, 255)).astype(np.uint8)
+    return np.stack([u8(r), u8(g), u8(b), np.full(hue.shape, 255, np.uint8)], axis=-1)
+
+
+@pytest.mark.parametrize("color_type", ["pressure", "speed"])
+def test_render_restatements_agree(color_type):
+    nx, ny = 60, 33
+    rng = np.random.default_rng(9)
+    kind, bu, bv = po.preset("obstacle", nx, ny)
+    o = po.OracleSim(nx, ny, delx=0.1, dely=0.2, delt=0.005, gamma=0.9, reynolds=100.0,
+                     sor_absolute_epsilon=1e-3, max_iterations=20, omega=1.7, kind=kind,
+                     bu=bu, bv=bv, p=rng.uniform(-3, 3, (nx, ny)), u=rng.uniform(-1, 1, (nx, ny)),
+                     v=rng.uniform(-1, 1, (nx, ny)))
+    o.run_simulation_tick()
+    st = o.state()
+    img = o.render_simulation(color_type)
+    if color_type == "pressure":
+        q, (lo, hi) = np.array(o.p), st.pressure_range
+    else:
+        q, (lo, hi) = np.sqrt(np.array(o.u) ** 2 + np.array(o.v) ** 2), st.speed_range
+    with np.errstate(invalid="ignore", divide="ignore"):
+        hue = 240.0 - (q - lo) * 240.0 / (hi - lo)
+    want = _hsl_numpy(hue)
+    wall = (127, 0, 0, 255) if color_type == "pressure" else (127, 127, 127, 255)
+    want[np.array(kind) != 0] = wall
+    assert np.array_equal(img, want.transpose(1, 0, 2))
