@@ -85,7 +85,7 @@ typedef struct {
     double initial_norm_squared;
     /* ---- extensions (0 = reference behaviour / defaults) ---- */
     double tau;                   /* > 0: adaptive delt (NaSt2D COMP_delt)       */
-    int32_t temporal_block;       /* red-black sweeps fused per pass, 1..4; 0 = default (3) */
+    int32_t temporal_block;       /* red-black sweeps fused per pass, 1..4; 0 = default (4) */
     int32_t device;               /* CUDA device ordinal; -1 = current device    */
     /* row-slab decomposition along x: this handle owns global rows
      * [x_begin, x_end) of the nx rows; 0,0 = whole grid.  Host arrays passed to

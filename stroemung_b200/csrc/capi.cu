@@ -93,7 +93,7 @@ static sb_status allocate(const sb_params *params, sb_sim **out) {
     sb_sim *s = new (std::nothrow) sb_sim();
     if (!s) return SB_INVALID_ARGUMENT;
     s->prm = *params;
-    if (s->prm.temporal_block == 0) s->prm.temporal_block = 3;
+    if (s->prm.temporal_block == 0) s->prm.temporal_block = 4;
     if (params->device >= 0) s->device = params->device;
     else cudaGetDevice(&s->device);
     cudaError_t e = cudaSetDevice(s->device);
@@ -688,7 +688,7 @@ sb_status sb_set_params(sb_sim *sim, const sb_params *p) {
     sim->prm.sor_absolute_epsilon = p->sor_absolute_epsilon; sim->prm.omega = p->omega;
     sim->prm.max_iterations = p->max_iterations; sim->prm.tau = p->tau;
     sim->prm.sor_mode = p->sor_mode;
-    sim->prm.temporal_block = p->temporal_block ? p->temporal_block : 3;
+    sim->prm.temporal_block = p->temporal_block ? p->temporal_block : 4;
     sim->time = p->time;
     sim->iterations = p->iterations;
     sim->has_initial_norm = p->has_initial_norm;

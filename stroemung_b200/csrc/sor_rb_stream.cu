@@ -52,7 +52,13 @@ constexpr int ROW_BYTES = SW * 8;
 //     after its row arrived and rows can be requested PF <= 4 ticks ahead.
 __host__ __device__ constexpr int stream_nw(int T) { return 2 * T + 4; }
 __host__ __device__ constexpr int stream_np(int T) { return T + 2; }
-__host__ __device__ constexpr int stream_pf(int T) { return T == 1 ? 2 : 3; }
+// rows requested ahead: <= T+1 (p ring) and <= 4 (rhs ring); measured best at 4 (profiles/)
+#ifndef SB_STREAM_PF
+#define SB_STREAM_PF 4
+#endif
+__host__ __device__ constexpr int stream_pf(int T) {
+    return SB_STREAM_PF < T + 1 ? SB_STREAM_PF : T + 1;
+}
 __host__ __device__ constexpr int stream_smem(int TB) {
     return (stream_np(TB) + stream_nw(TB)) * ROW_BYTES + stream_nw(TB) * 8;
 }
