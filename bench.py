@@ -288,6 +288,7 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
     pass_ms = sim.profile_read()
+    rb_plan = list(sim.rb_plan) if args.mode == "rb" else None
     sim.profile_enable(False)
     launches = sim.kernel_launches - launches0
     dt, sor_ms = max_over_ranks(dt), max_over_ranks(sor_ms)
@@ -369,6 +370,8 @@ def run_ours(args):
         "config": {"workload": wl["name"], "grid": [nx, ny], "sor_mode": args.mode,
                    "temporal_block": T, "sweeps_per_tick": k_avg,
                    "slabs": f"{n_gpus} row slab(s) along x",
+                   "rb_plan": {"tile_kernel_tiles": rb_plan[0], "stream_items": rb_plan[1]}
+                   if rb_plan else None,
                    "l2": "working set 3.8 GB per GPU >> 126 MB L2, no flush needed"},
         "sor": {"gcell_sweeps_per_s": cells * total_sweeps / (sor_ms * 1e-3) / 1e9
                 if sor_ms else None,

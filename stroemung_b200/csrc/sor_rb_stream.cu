@@ -1,13 +1,15 @@
-// sor_rb_stream.cu -- K4c: the performance-mode SOR pass on all-fluid regions, as a
+// sor_rb_stream.cu -- K4c: the performance-mode SOR pass on regular regions, as a
 // register-resident row pipeline ("2.5-D" temporal blocking).
 //
 // Same arithmetic as the tile kernel (sor_rb.cuh; the red-black restatement of the sweep of
-// /root/reference/src/simulation.rs:253-274 and of calculate_norm_squared, :216-227), other
-// schedule.  Where the footprint of a piece of the grid holds nothing but interior fluid
-// cells with fluid neighbours, no pressure BC and no cell test is needed, and T sweeps can
-// be pipelined along x by ONE WARP without any block-level synchronisation:
+// /root/reference/src/simulation.rs:253-274, of copy_pressure_to_boundaries,
+// src/grid/mod.rs:343-412, and of calculate_norm_squared, simulation.rs:216-227), other
+// schedule.  Where a piece of the grid holds nothing but fluid cells -- plus, optionally, ONE
+// straight wall along x on the strip's first or last column and a boundary row (inflow,
+// outflow, wall) at either end in x -- T sweeps can be pipelined along x by ONE WARP without
+// any block-level synchronisation:
 //
-//   * a warp owns a 128-column strip (4 adjacent columns per lane) and walks down x;
+//   * a warp owns a 128-column strip (4 columns per lane) and walks down x;
 //   * in the tick in which row R arrives it runs, for k = 0..T-1, the red half-sweep of
 //     sweep k on row R-(2k+1) and the black half-sweep on row R-(2k+2) (each needs its two
 //     neighbour rows one half-sweep behind -- true in this order), then the residual of the
@@ -16,21 +18,33 @@
 //     every row has a fixed register name); the only exchange between lanes is one shuffle
 //     per half-sweep (the y-neighbour across the lane boundary);
 //   * rows of p and rhs are fetched PF rows ahead by 1-D bulk copies of the TMA engine into
-//     per-warp shared-memory rings (mbarrier per slot); rhs stays in its ring for the 2T+2
-//     ticks a row is worked on;
+//     per-warp shared-memory rings (one mbarrier per slot);
 //   * residuals ride along exactly as in the tile kernel: black cells at their update, red
 //     cells of sweep k inside the red half-sweep of sweep k+1.
 //
-// Halo: the strip carries h = 2T+2 columns per side like a tile, but along x only the two
-// ends of a work item pay 2T+2 warm-up rows -- a tile pays them every 48 rows.  Useful work
-// per cell update rises from 58 % (T = 3 tile) to ~80 %, and there is no load phase: loads,
-// arithmetic and stores of different rows overlap all the time.
+// Boundary cells inside an item.  The reference copies pressures into the boundary cells
+// once per iteration, BEFORE the sweep (simulation.rs:251).  A wall cell (x, 0) takes
+// p(x, 1); it sits in the register window like any other cell (lane 0's first / lane 31's
+// last cell), is refreshed at the start of the red half-sweep of its row, never updated and
+// never counted.  A boundary row at the end of an item (grid row 0 or NX-1) is refreshed from
+// its neighbour row at the start of that row's red half-sweep.  The one subtlety is the late
+// red residual: the residual of sweep k-1 of a red cell next to a boundary cell must see the
+// boundary value of sweep k-1, so in those half-sweeps the stencil sum is taken first with
+// the old boundary value (residual), then the boundary cell is refreshed and the affected sum
+// retaken (update).  Walls are a template parameter (plain strips carry none of this code);
+// boundary rows only exist in the warm-up / drain path of an item.
+//
+// Halo: a strip carries h = 2T+2 columns per open side like a tile, but along x only the
+// open ends of a work item pay 2T+2 warm-up rows -- a tile pays them every 48 rows.
 //
 // HBM traffic per item and cell: 8 (p) + 8 (rhs) + 8 (p out) = 24 B for T sweeps (+ the
 // strip halo re-reads, L2 hits when neighbouring strips run side by side).
 //
-// Which tiles are "plain" is decided per lattice tile by rb_plain_kernel; the host turns
-// runs of plain tiles along x into work items (RbPlan).
+// What kind of item a lattice tile can join is decided per tile by rb_class_kernel; the host
+// turns runs of equal tiles along x into work items (RbPlan).  Everything else -- obstacles,
+// corners of walls, slab edges -- stays with the tile kernel.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "sor_rb.cuh"
@@ -41,6 +55,13 @@ namespace {
 
 constexpr int SW = RB_TW;      // strip columns: 32 lanes x 2 pairs of columns
 constexpr int ROW_BYTES = SW * 8;
+
+// item kinds (RbItem::pad bits 0-1) and flags
+constexpr int IT_PLAIN = 0, IT_WALL_LO = 1, IT_WALL_HI = 2;
+constexpr int IT_BC_LO = 4;    // the item's first row is a boundary row fed from the next row
+constexpr int IT_BC_HI = 8;    // the item's last row is a boundary row fed from the row before
+// tile classes of rb_class_kernel: 0 = tile kernel, 1 + item kind otherwise, plus
+constexpr int TC_BC_LO = 4, TC_BC_HI = 8;  // the tile owns grid row 0 / NX-1 as such a row
 
 // Everything that indexes a ring is a compile-time constant inside the unrolled window:
 //   * the tick loop is unrolled over NW = 2T+4 ticks (the register window), U = tick mod NW;
@@ -59,15 +80,30 @@ __host__ __device__ constexpr int stream_np(int T) { return T + 2; }
 __host__ __device__ constexpr int stream_pf(int T) {
     return SB_STREAM_PF < T + 1 ? SB_STREAM_PF : T + 1;
 }
+// shared memory of one warp (rings + mbarriers), padded to the 128-byte ring alignment
 __host__ __device__ constexpr int stream_smem(int TB) {
-    return (stream_np(TB) + stream_nw(TB)) * ROW_BYTES + stream_nw(TB) * 8;
+    return ((stream_np(TB) + stream_nw(TB)) * ROW_BYTES + stream_nw(TB) * 8 + 127) / 128 * 128;
 }
 // warps per SM the register budget of the TB instantiation is cut for.  The register file
 // is split per SM sub-partition (16 K registers each), so the steps are 16 warps (128
 // registers per thread), 12 (168) and 8 (255): TB = 4 keeps 48 pressures per lane in flight
 // and needs the last one.
-__host__ __device__ constexpr int stream_min_ctas(int TB) {
+__host__ __device__ constexpr int stream_warps(int TB) {
     return TB == 1 ? 16 : TB <= 3 ? 12 : 8;
+}
+// All warps of an SM form ONE CTA (they never synchronise with each other) whose items are
+// all of the same kind.  The unrolled window of one kind is 32 KB (T = 3) to 50 KB (T = 4) of
+// code against 32 KB of L1.5 instruction cache per SM: warps of different kinds on one SM
+// evict each other's loop -- measured (profiles/r1_stream_kinds_ab.txt) a pass with 3 % of
+// wall items scattered over the SMs takes 0.63 ms, the same items all on one code path 0.43.
+
+// SB_STREAM_TRACE=1: per item of the last pass: start, end (globaltimer ns), SM, kind
+__device__ unsigned long long g_trace[4096 * 4];
+__device__ int g_trace_on;
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -84,10 +120,14 @@ struct SCtx {
     const double *pin, *rhs;   // first column of the strip in local row 0
     double *pout;
     int64_t pitch;
-    int x0, x1;                // rows counted and stored
+    int x0, x1;                // rows stored
+    int cx0, cx1;              // rows swept and counted (the stored rows minus boundary rows)
+    int bc_lo, bc_hi;          // boundary rows of the item (far out of range if none)
     int first, re;             // rows loaded: [first, re)
+    int rend;                  // ticks run for rows [rs, rend): rend = x1 + 2T+2 (drain)
     int lane, lane_m1, lane_p1;
-    bool cmA, cmB;             // the pair lies in the strip's inner columns [h, SW-h)
+    bool cmA, cmB;             // the pair lies in the strip's stored / counted columns
+    bool keepA, keepB;         // A0 / B1 of this lane is a wall cell
     double *pring, *rring;     // ring bases
     const double *pl, *rl;     // this lane's pair A in slot 0 of the p / rhs ring
     uint64_t *bar;
@@ -103,35 +143,124 @@ __device__ __forceinline__ void issue_row(const SCtx &c, int64_t off, int slot) 
     bulk_load(c.rring + slot * SW, c.rhs + off, ROW_BYTES, bar);
 }
 
-// stencil sums t of the two cells of one colour in a lane's two column pairs.
-// SET 0: the first cells A0, B0 (y-neighbours: the lane's own second cell and the second cell
-// of the pair to the left), SET 1: the second cells A1, B1 (own first cell, first cell of the
+// The two cells of one colour in a lane's two column pairs.  SET 0: the first cells A0, B0
+// (cells 0, 2; y-neighbours: the lane's own second cell and the second cell of the pair to
+// the left), SET 1: the second cells A1, B1 (cells 1, 3; own first cell, first cell of the
 // pair to the right).  Pair B of lane 0 continues pair A of lane 31 and vice versa.
+// nbr2: the two foreign y-neighbours.
 template <int SET>
-__device__ __forceinline__ void stencil2(const SCtx &c, const double (&me)[4],
-                                         const double (&up)[4], const double (&dn)[4],
-                                         double rha, double rhb, double &ta, double &tb) {
-    const RbConsts &k = c.k;
+__device__ __forceinline__ void nbr2(const SCtx &c, const double (&me)[4], double &na,
+                                     double &nb) {
     if (SET == 0) {
         const double la = __shfl_sync(0xffffffffu, me[1], c.lane_m1);
         const double lb0 = __shfl_sync(0xffffffffu, me[3], c.lane_m1);
-        const double lb = c.lane == 0 ? la : lb0;
-        ta = fma(k.rdx2, dn[0] + up[0], fma(k.rdy2, me[1] + la, -rha));
-        tb = fma(k.rdx2, dn[2] + up[2], fma(k.rdy2, me[3] + lb, -rhb));
+        na = la;
+        nb = c.lane == 0 ? la : lb0;
     } else {
         const double ra0 = __shfl_sync(0xffffffffu, me[0], c.lane_p1);
         const double rb = __shfl_sync(0xffffffffu, me[2], c.lane_p1);
-        const double ra = c.lane == 31 ? rb : ra0;
-        ta = fma(k.rdx2, dn[1] + up[1], fma(k.rdy2, ra + me[0], -rha));
-        tb = fma(k.rdx2, dn[3] + up[3], fma(k.rdy2, rb + me[2], -rhb));
+        na = c.lane == 31 ? rb : ra0;
+        nb = rb;
+    }
+}
+// t = fma(1/dx^2, pE + pW, fma(1/dy^2, pS + pN, -rhs))
+__device__ __forceinline__ double tsum(const RbConsts &k, double xs, double ys, double rh) {
+    return fma(k.rdx2, xs, fma(k.rdy2, ys, -rh));
+}
+
+// One half-sweep of sweep kk (RED: first colour) on the row in register slot s, cells SET.
+//   RED:   rhs from the ring (the other colour's values are carried to the black half-sweep
+//          of the next tick); the residuals of sweep kk-1 of these cells are taken here, one
+//          sweep late (LATE = kk > 0, into acc*[kk-1]); boundary cells are refreshed.
+//   black: rhs carried; residuals of sweep kk right after the update.
+// q = the row; STEADY: q is an ordinary counted row (no row tests).
+template <int T, bool STEADY, int WALL, int SET, bool RED>
+__device__ __forceinline__ void half_sweep(double (&W)[2 * T + 4][4], const int s, const int q,
+                                           const int kk, const double rha, const double rhb,
+                                           double &acc_a, double &acc_b, const SCtx &c) {
+    constexpr int NW = stream_nw(T);
+    constexpr int ia = SET, ib = SET + 2, oa = SET ^ 1, ob = (SET ^ 1) + 2;
+    // the wall cell is one of these cells / the fluid cell next to the wall is
+    constexpr bool wall_a = WALL == IT_WALL_LO && SET == 0;   // cell 0 of lane 0
+    constexpr bool wall_b = WALL == IT_WALL_HI && SET == 1;   // cell 3 of lane 31
+    constexpr bool adj_a = WALL == IT_WALL_LO && SET == 1;    // cell 1 of lane 0
+    constexpr bool adj_b = WALL == IT_WALL_HI && SET == 0;    // cell 2 of lane 31
+    const RbConsts &k = c.k;
+    const int sm = (s + NW - 1) % NW, sp = (s + 1) % NW;
+    if (!STEADY && (q == c.bc_lo || q == c.bc_hi)) return;   // a boundary row: not swept
+    const bool rv = STEADY || (unsigned)(q - c.cx0) < (unsigned)(c.cx1 - c.cx0);
+    const bool late = RED && kk > 0;
+    // boundary refresh of this iteration (red half-sweep only): wall cell <- its fluid
+    // neighbour; boundary row <- this row (corner cells on the wall column keep their value)
+    const bool row_lo = !STEADY && RED && q == c.bc_lo + 1;
+    const bool row_hi = !STEADY && RED && q == c.bc_hi - 1;
+    auto refresh_wall = [&]() {
+        if (WALL == IT_WALL_LO) W[s][0] = c.keepA ? W[s][1] : W[s][0];
+        if (WALL == IT_WALL_HI) W[s][3] = c.keepB ? W[s][2] : W[s][3];
+    };
+    auto refresh_rows = [&]() {
+        if (row_lo) {
+            W[sm][0] = (WALL == IT_WALL_LO && c.keepA) ? W[sm][0] : W[s][0];
+            W[sm][1] = W[s][1];
+            W[sm][2] = W[s][2];
+            W[sm][3] = (WALL == IT_WALL_HI && c.keepB) ? W[sm][3] : W[s][3];
+        }
+        if (row_hi) {
+            W[sp][0] = (WALL == IT_WALL_LO && c.keepA) ? W[sp][0] : W[s][0];
+            W[sp][1] = W[s][1];
+            W[sp][2] = W[s][2];
+            W[sp][3] = (WALL == IT_WALL_HI && c.keepB) ? W[sp][3] : W[s][3];
+        }
+    };
+    if (RED && !late) {  // first sweep of the pass: nothing is late, refresh first
+        refresh_wall();
+        if (!STEADY) refresh_rows();
+    }
+    if (RED && late && !(adj_a || adj_b)) refresh_wall();  // no counted cell sees the wall here
+    double na, nb;
+    nbr2<SET>(c, W[s], na, nb);
+    double xa = W[sp][ia] + W[sm][ia], xb = W[sp][ib] + W[sm][ib];
+    double ta = tsum(k, xa, W[s][oa] + na, rha), tb = tsum(k, xb, W[s][ob] + nb, rhb);
+    if (late) {
+        if (rv) {  // residuals of sweep kk-1 with the boundary values of sweep kk-1
+            double ra = fma(-k.diag, W[s][ia], ta), rb = fma(-k.diag, W[s][ib], tb);
+            if (wall_a) ra = c.keepA ? 0.0 : ra;
+            if (wall_b) rb = c.keepB ? 0.0 : rb;
+            acc_a = fma(ra, ra, acc_a);
+            acc_b = fma(rb, rb, acc_b);
+        }
+        if (adj_a || adj_b) {  // now the wall cell moves on to sweep kk: retake the sum
+            refresh_wall();
+            if (adj_a) ta = tsum(k, xa, W[s][oa] + na, rha);
+            if (adj_b) tb = tsum(k, xb, W[s][ob] + nb, rhb);
+        }
+        if (!STEADY && (row_lo || row_hi)) {  // warp-uniform
+            refresh_rows();
+            xa = W[sp][ia] + W[sm][ia];
+            xb = W[sp][ib] + W[sm][ib];
+            ta = tsum(k, xa, W[s][oa] + na, rha);
+            tb = tsum(k, xb, W[s][ob] + nb, rhb);
+        }
+    }
+    double pa = fma(k.mid, ta, k.omw * W[s][ia]), pb = fma(k.mid, tb, k.omw * W[s][ib]);
+    if (wall_a) pa = c.keepA ? W[s][ia] : pa;
+    if (wall_b) pb = c.keepB ? W[s][ib] : pb;
+    W[s][ia] = pa;
+    W[s][ib] = pb;
+    if (!RED && rv) {
+        double ra = fma(-k.diag, pa, ta), rb = fma(-k.diag, pb, tb);
+        if (wall_a) ra = c.keepA ? 0.0 : ra;
+        if (wall_b) rb = c.keepB ? 0.0 : rb;
+        acc_a = fma(ra, ra, acc_a);
+        acc_b = fma(rb, rb, acc_b);
     }
 }
 
 // One tick: row R has been requested PF ticks ago.  U = (R - rs) mod NW is the register slot
 // of row R and its ring slot; after inlining into the unrolled loop every index below is a
 // constant.  roff = R * pitch.  ph = parity of the mbarrier phase of this loop iteration.
-// STEADY: every row this tick touches is a counted row (no row tests at all).
-template <int T, bool STEADY>
+// STEADY: every row this tick touches is an ordinary counted row (no row tests at all).
+template <int T, bool STEADY, int WALL>
 __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&C)[T][2],
                                             double (&FR)[2][2], double (&accA)[T],
                                             double (&accB)[T], const int U, const int R,
@@ -139,14 +268,13 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
                                             const SCtx &c) {
     constexpr int NW = stream_nw(T), NP = stream_np(T), PF = stream_pf(T);
     const RbConsts &k = c.k;
-    const unsigned nrows = (unsigned)(c.x1 - c.x0);
     // ---- request row R + PF; row R: shared-memory ring -> registers ------------------------
     __syncwarp();  // every lane is done with the slots the request overwrites
     if (c.lane == 0) {
         if (STEADY || R + PF < c.re) issue_row<NP>(c, roff + PF * c.pitch, (U + PF) % NW);
         if (!STEADY && R < c.first) mbar_arrive(c.bar + U);  // keeps the phases in step
     }
-    if (STEADY || R >= c.first) {
+    if (STEADY || (R >= c.first && R < c.re)) {
         mbar_wait(c.bar + U, ph);
         const double *src = c.pl + (U % NP) * SW;
         const double2 a = *reinterpret_cast<const double2 *>(src);
@@ -158,96 +286,64 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
     double fr_a = 0.0, fr_b = 0.0;  // red rhs of the row of the last red half-sweep
 #pragma unroll
     for (int kk = 0; kk < T; kk++) {
-        // ---- red half-sweep of sweep kk on row R - (2kk+1) ---------------------------------
         double carry_a, carry_b;
         const int lv = kk > 0 ? kk - 1 : 0;  // level of the late red residuals
-        {
+        {   // ---- red half-sweep of sweep kk on row R - (2kk+1) -----------------------------
             const int lag = 2 * kk + 1;
-            const int s = (U + 2 * NW - lag) % NW, sm = (s + NW - 1) % NW, sp = (s + 1) % NW;
-            const int par = s & 1;  // row parity (rs has even global x, NW is even)
-            const int q = R - lag;
+            const int s = (U + 2 * NW - lag) % NW;
             const double *rp = c.rl + s * SW;
             const double2 rA = *reinterpret_cast<const double2 *>(rp);
             const double2 rB = *reinterpret_cast<const double2 *>(rp + 64);
-            const bool rv = STEADY || (unsigned)(q - c.x0) < nrows;
-            double ta, tb;
-            if (par == 0) {
-                stencil2<0>(c, W[s], W[sm], W[sp], rA.x, rB.x, ta, tb);
-                if (kk > 0 && rv) {  // residuals of sweep kk-1, one sweep late
-                    const double ra = fma(-k.diag, W[s][0], ta), rb = fma(-k.diag, W[s][2], tb);
-                    accA[lv] = fma(ra, ra, accA[lv]);
-                    accB[lv] = fma(rb, rb, accB[lv]);
-                }
-                W[s][0] = fma(k.mid, ta, k.omw * W[s][0]);
-                W[s][2] = fma(k.mid, tb, k.omw * W[s][2]);
+            if ((s & 1) == 0) {  // row parity (rs has even global x, NW is even)
+                half_sweep<T, STEADY, WALL, 0, true>(W, s, R - lag, kk, rA.x, rB.x, accA[lv],
+                                                     accB[lv], c);
                 carry_a = rA.y; carry_b = rB.y;
                 if (kk == T - 1) { fr_a = rA.x; fr_b = rB.x; }
             } else {
-                stencil2<1>(c, W[s], W[sm], W[sp], rA.y, rB.y, ta, tb);
-                if (kk > 0 && rv) {
-                    const double ra = fma(-k.diag, W[s][1], ta), rb = fma(-k.diag, W[s][3], tb);
-                    accA[lv] = fma(ra, ra, accA[lv]);
-                    accB[lv] = fma(rb, rb, accB[lv]);
-                }
-                W[s][1] = fma(k.mid, ta, k.omw * W[s][1]);
-                W[s][3] = fma(k.mid, tb, k.omw * W[s][3]);
+                half_sweep<T, STEADY, WALL, 1, true>(W, s, R - lag, kk, rA.y, rB.y, accA[lv],
+                                                     accB[lv], c);
                 carry_a = rA.x; carry_b = rB.x;
                 if (kk == T - 1) { fr_a = rA.y; fr_b = rB.y; }
             }
         }
-        // ---- black half-sweep of sweep kk on row R - (2kk+2); rhs carried from last tick ---
-        {
+        {   // ---- black half-sweep of sweep kk on row R - (2kk+2); rhs carried one tick ------
             const int lag = 2 * kk + 2;
-            const int s = (U + 2 * NW - lag) % NW, sm = (s + NW - 1) % NW, sp = (s + 1) % NW;
-            const int par = s & 1;
-            const int q = R - lag;
-            const bool rv = STEADY || (unsigned)(q - c.x0) < nrows;
-            double ta, tb;
-            if (par == 0) {  // black cells of an even row: the second cells
-                stencil2<1>(c, W[s], W[sm], W[sp], C[kk][0], C[kk][1], ta, tb);
-                const double pa = fma(k.mid, ta, k.omw * W[s][1]);
-                const double pb = fma(k.mid, tb, k.omw * W[s][3]);
-                W[s][1] = pa; W[s][3] = pb;
-                if (rv) {
-                    const double ra = fma(-k.diag, pa, ta), rb = fma(-k.diag, pb, tb);
-                    accA[kk] = fma(ra, ra, accA[kk]);
-                    accB[kk] = fma(rb, rb, accB[kk]);
-                }
-            } else {
-                stencil2<0>(c, W[s], W[sm], W[sp], C[kk][0], C[kk][1], ta, tb);
-                const double pa = fma(k.mid, ta, k.omw * W[s][0]);
-                const double pb = fma(k.mid, tb, k.omw * W[s][2]);
-                W[s][0] = pa; W[s][2] = pb;
-                if (rv) {
-                    const double ra = fma(-k.diag, pa, ta), rb = fma(-k.diag, pb, tb);
-                    accA[kk] = fma(ra, ra, accA[kk]);
-                    accB[kk] = fma(rb, rb, accB[kk]);
-                }
-            }
+            const int s = (U + 2 * NW - lag) % NW;
+            if ((s & 1) == 0)  // black cells of an even row: the second cells
+                half_sweep<T, STEADY, WALL, 1, false>(W, s, R - lag, kk, C[kk][0], C[kk][1],
+                                                      accA[kk], accB[kk], c);
+            else
+                half_sweep<T, STEADY, WALL, 0, false>(W, s, R - lag, kk, C[kk][0], C[kk][1],
+                                                      accA[kk], accB[kk], c);
         }
         C[kk][0] = carry_a;
         C[kk][1] = carry_b;
     }
     // ---- residual of the red cells of the last sweep on row R - (2T+1); its red rhs values
-    //      were read two ticks ago (FR[U & 1]) ------------------------------------------------
+    //      were read two ticks ago (FR[U & 1]); no boundary cell has been refreshed since ------
     {
         const int lag = 2 * T + 1;
         const int s = (U + 2 * NW - lag) % NW, sm = (s + NW - 1) % NW, sp = (s + 1) % NW;
-        const int par = s & 1;
         const int q = R - lag;
-        if (STEADY || (unsigned)(q - c.x0) < nrows) {  // warp-uniform
-            double ta, tb;
-            if (par == 0) {
-                stencil2<0>(c, W[s], W[sm], W[sp], FR[U & 1][0], FR[U & 1][1], ta, tb);
-                const double ra = fma(-k.diag, W[s][0], ta), rb = fma(-k.diag, W[s][2], tb);
-                accA[T - 1] = fma(ra, ra, accA[T - 1]);
-                accB[T - 1] = fma(rb, rb, accB[T - 1]);
+        if (STEADY || (unsigned)(q - c.cx0) < (unsigned)(c.cx1 - c.cx0)) {  // warp-uniform
+            double na, nb, ra, rb;
+            if ((s & 1) == 0) {
+                nbr2<0>(c, W[s], na, nb);
+                ra = fma(-k.diag, W[s][0],
+                         tsum(k, W[sp][0] + W[sm][0], W[s][1] + na, FR[U & 1][0]));
+                rb = fma(-k.diag, W[s][2],
+                         tsum(k, W[sp][2] + W[sm][2], W[s][3] + nb, FR[U & 1][1]));
+                if (WALL == IT_WALL_LO) ra = c.keepA ? 0.0 : ra;
             } else {
-                stencil2<1>(c, W[s], W[sm], W[sp], FR[U & 1][0], FR[U & 1][1], ta, tb);
-                const double ra = fma(-k.diag, W[s][1], ta), rb = fma(-k.diag, W[s][3], tb);
-                accA[T - 1] = fma(ra, ra, accA[T - 1]);
-                accB[T - 1] = fma(rb, rb, accB[T - 1]);
+                nbr2<1>(c, W[s], na, nb);
+                ra = fma(-k.diag, W[s][1],
+                         tsum(k, W[sp][1] + W[sm][1], W[s][0] + na, FR[U & 1][0]));
+                rb = fma(-k.diag, W[s][3],
+                         tsum(k, W[sp][3] + W[sm][3], W[s][2] + nb, FR[U & 1][1]));
+                if (WALL == IT_WALL_HI) rb = c.keepB ? 0.0 : rb;
             }
+            accA[T - 1] = fma(ra, ra, accA[T - 1]);
+            accB[T - 1] = fma(rb, rb, accB[T - 1]);
         }
         FR[U & 1][0] = fr_a;
         FR[U & 1][1] = fr_b;
@@ -257,7 +353,7 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
         const int lag = 2 * T + 2;
         const int s = (U + 2 * NW - lag) % NW;
         const int q = R - lag;
-        if (STEADY || (unsigned)(q - c.x0) < nrows) {
+        if (STEADY || (unsigned)(q - c.x0) < (unsigned)(c.x1 - c.x0)) {
             double *dst = c.pout + (roff - lag * c.pitch);
             if (c.cmA) stg_f64x2(dst, W[s][0], W[s][1]);
             if (c.cmB) stg_f64x2(dst + 64, W[s][2], W[s][3]);
@@ -265,17 +361,27 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
     }
 }
 
-template <int T>
-__device__ __forceinline__ void stream_item(SCtx &c, int gpar, double *__restrict__ partial,
-                                            int64_t part_stride) {
+template <int T, int WALL>
+__device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
+                                            double *__restrict__ partial, int64_t part_stride) {
     constexpr int NW = stream_nw(T), NP = stream_np(T), PF = stream_pf(T);
     constexpr int HP = 2 * T + 2;
-    c.first = c.x0 - HP;
-    c.re = c.x1 + HP;
+    const bool lo = flags & IT_BC_LO, hi = flags & IT_BC_HI;
+    c.first = lo ? c.x0 : c.x0 - HP;
+    c.re = hi ? c.x1 : c.x1 + HP;
+    c.rend = c.x1 + HP;
+    c.bc_lo = lo ? c.x0 : -(1 << 29);
+    c.bc_hi = hi ? c.x1 - 1 : (1 << 29);
+    c.cx0 = c.x0 + (lo ? 1 : 0);
+    c.cx1 = c.x1 - (hi ? 1 : 0);
+    c.keepA = WALL == IT_WALL_LO && c.lane == 0;
+    c.keepB = WALL == IT_WALL_HI && c.lane == 31;
     // the tick loop starts on a row of even global x so that register slot parity = row parity
     const int rs = c.first - ((gpar + c.first) & 1);
-    // ticks R in [st_lo, st_hi]: all rows R-1 .. R-(2T+2) lie in [x0, x1)
-    const int st_lo = c.x0 + 2 * T + 2, st_hi = c.x1;
+    // steady ticks R in [st_lo, st_hi]: rows R-1 .. R-(2T+2) are ordinary counted rows (not
+    // next to a boundary row either) and row R + PF is still to be requested
+    const int st_lo = c.x0 + (lo ? 2 : 0) + 2 * T + 2;
+    const int st_hi = min(c.x1 - (hi ? 2 : 0), c.re - PF - 1);
     if (c.lane == 0) {
         for (int i = 0; i < NW; i++) mbar_init(c.bar + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -292,12 +398,12 @@ __device__ __forceinline__ void stream_item(SCtx &c, int gpar, double *__restric
     FR[0][0] = FR[0][1] = FR[1][0] = FR[1][1] = 0.0;
     uint32_t ph = 0;
     int64_t roff = (int64_t)rs * c.pitch;
-    for (int R0 = rs; R0 < c.re;) {
+    for (int R0 = rs; R0 < c.rend;) {
         if (R0 >= st_lo && R0 + NW - 1 <= st_hi) {
             do {  // the steady state: straight-line code, no row tests
 #pragma unroll
                 for (int U = 0; U < NW; U++) {
-                    stream_tick<T, true>(W, C, FR, accA, accB, U, R0 + U, roff, ph, c);
+                    stream_tick<T, true, WALL>(W, C, FR, accA, accB, U, R0 + U, roff, ph, c);
                     roff += c.pitch;
                 }
                 ph ^= 1u;
@@ -306,8 +412,8 @@ __device__ __forceinline__ void stream_item(SCtx &c, int gpar, double *__restric
         } else {
 #pragma unroll
             for (int U = 0; U < NW; U++) {
-                if (R0 + U >= c.re) break;
-                stream_tick<T, false>(W, C, FR, accA, accB, U, R0 + U, roff, ph, c);
+                if (R0 + U >= c.rend) break;
+                stream_tick<T, false, WALL>(W, C, FR, accA, accB, U, R0 + U, roff, ph, c);
                 roff += c.pitch;
             }
             ph ^= 1u;
@@ -321,25 +427,46 @@ __device__ __forceinline__ void stream_item(SCtx &c, int gpar, double *__restric
     }
 }
 
-// one warp per CTA, one work item per warp; TB = the configured temporal block (the lattice
-// and the shared-memory budget follow it), the pass itself runs ctl->active_T <= TB sweeps
+template <int T>
+__device__ __forceinline__ void stream_item_any(SCtx &c, int flags, int gpar, double *partial,
+                                                int64_t part_stride) {
+    const int wall = flags & 3;
+    if (wall == IT_PLAIN) stream_item<T, IT_PLAIN>(c, flags, gpar, partial, part_stride);
+    else if (wall == IT_WALL_LO) stream_item<T, IT_WALL_LO>(c, flags, gpar, partial, part_stride);
+    else stream_item<T, IT_WALL_HI>(c, flags, gpar, partial, part_stride);
+}
+
+// one work item per warp, stream_warps(TB) warps per CTA, one CTA per SM; TB = the configured
+// temporal block (the lattice and the shared-memory budget follow it), the pass itself runs
+// ctl->active_T <= TB sweeps.  Items with x1 <= x0 pad a CTA to one kind.
 template <int TB>
-__global__ void __launch_bounds__(32, stream_min_ctas(TB))
+__global__ void __launch_bounds__(32 * stream_warps(TB), 1)
 sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict__ pbuf,
                      const double *__restrict__ rhs, const SorCtl *__restrict__ ctl,
                      double *__restrict__ partial, int part_base, int part_stride, int64_t pitch,
-                     int gpar, int h, RbConsts k) {
+                     int gpar, RbConsts k) {
     const int T = ctl->active_T;
     if (T == 0) return;
     const int src = ctl->src;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const RbItem it = items[blockIdx.x];
+    // broadcast from lane 0: tells the compiler the warp index (and all that follows from
+    // it: ring addresses, item fields) is warp-uniform, so it stays on the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int idx = blockIdx.x * stream_warps(TB) + warp;
+    const RbItem it = items[idx];
+    const int flags = it.pad & 0xff, st0 = (it.pad >> 8) & 0xff, st1 = (it.pad >> 16) & 0xff;
     SCtx c;
-    c.lane = threadIdx.x;
+    c.lane = threadIdx.x & 31;
+    double *part = partial + part_base + idx;
+    if (it.x1 <= it.x0) {  // padding: contributes nothing
+        if (c.lane == 0)
+            for (int i = 0; i < T; i++) part[(int64_t)i * part_stride] = 0.0;
+        return;
+    }
     c.lane_m1 = (c.lane + 31) & 31;
     c.lane_p1 = (c.lane + 1) & 31;
     // rings of the T actually run: p ring, rhs ring, one mbarrier per rhs slot
-    c.pring = reinterpret_cast<double *>(smem_raw);
+    c.pring = reinterpret_cast<double *>(smem_raw + warp * stream_smem(TB));
     c.rring = c.pring + stream_np(T) * SW;
     c.bar = reinterpret_cast<uint64_t *>(c.rring + stream_nw(T) * SW);
     c.pl = c.pring + 2 * c.lane;
@@ -351,17 +478,27 @@ sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict
     c.x0 = it.x0;
     c.x1 = it.x1;
     c.k = k;
-    c.cmA = 2 * c.lane >= h && 2 * c.lane < SW - h;
-    c.cmB = 64 + 2 * c.lane >= h && 64 + 2 * c.lane < SW - h;
-    double *part = partial + part_base + blockIdx.x;
-    if (T == TB) stream_item<TB>(c, gpar, part, part_stride);
-    else if (TB > 1 && T == 1) stream_item<1>(c, gpar, part, part_stride);
-    else if (TB > 2 && T == 2) stream_item<2>(c, gpar, part, part_stride);
-    else if (TB > 3 && T == 3) stream_item<3>(c, gpar, part, part_stride);
+    // stored = counted columns [st0, st1) of the strip (pair-aligned; a wall cell inside is
+    // stored but not counted: keepA / keepB)
+    c.cmA = 2 * c.lane >= st0 && 2 * c.lane < st1;
+    c.cmB = 64 + 2 * c.lane >= st0 && 64 + 2 * c.lane < st1;
+    const bool trace = g_trace_on && idx < 4096;
+    if (trace && c.lane == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_trace[4 * idx] = gtime();
+        g_trace[4 * idx + 2] = smid;
+        g_trace[4 * idx + 3] = (unsigned)flags | ((unsigned long long)(it.x1 - it.x0) << 8);
+    }
+    if (T == TB) stream_item_any<TB>(c, flags, gpar, part, part_stride);
+    else if (TB > 1 && T == 1) stream_item_any<1>(c, flags, gpar, part, part_stride);
+    else if (TB > 2 && T == 2) stream_item_any<2>(c, flags, gpar, part, part_stride);
+    else if (TB > 3 && T == 3) stream_item_any<3>(c, flags, gpar, part, part_stride);
+    if (trace && c.lane == 0) g_trace[4 * idx + 1] = gtime();
 }
 
 using StreamKernel = void (*)(const RbItem *, double *const *, const double *, const SorCtl *,
-                              double *, int, int, int64_t, int, int, RbConsts);
+                              double *, int, int, int64_t, int, RbConsts);
 StreamKernel stream_kernel(int TB) {
     switch (TB) {
     case 1: return sor_rb_stream_kernel<1>;
@@ -370,42 +507,93 @@ StreamKernel stream_kernel(int TB) {
     default: return sor_rb_stream_kernel<4>;
     }
 }
+int stream_cta_warps(int TB) {
+    switch (TB) {
+    case 1: return stream_warps(1);
+    case 2: return stream_warps(2);
+    case 3: return stream_warps(3);
+    default: return stream_warps(4);
+    }
+}
+// dynamic shared memory of one CTA
 int stream_smem_bytes(int TB) {
     switch (TB) {
-    case 1: return stream_smem(1);
-    case 2: return stream_smem(2);
-    case 3: return stream_smem(3);
-    default: return stream_smem(4);
+    case 1: return stream_smem(1) * stream_warps(1);
+    case 2: return stream_smem(2) * stream_warps(2);
+    case 3: return stream_smem(3) * stream_warps(3);
+    default: return stream_smem(4) * stream_warps(4);
     }
 }
 
-// plain[tile] = 1 iff every cell of the tile's footprint (inner region + h cells around it,
-// 128 columns wide) is an interior fluid cell without a non-fluid neighbour
-__global__ void rb_plain_kernel(const uint8_t *__restrict__ cflag, Geom g, int tiles_y, int BX,
-                                int BY, int h, uint8_t *__restrict__ plain) {
+// Class of every lattice tile (BX x BY inner region, h cells of footprint around it), decided
+// on the cells of the 128-column strip an item of that tile would run on:
+//   tiles of the first / last tile column: strip [0, 128) / [NY-128, NY) -- the wall column
+//   must hold boundary cells fed from their y-neighbour (edge class S / N) and nothing else
+//   may be a boundary cell; other tiles: strip [tj BY - h, ..+128), all fluid;
+//   grid rows 0 and NX-1, if the tile owns them, must hold boundary cells fed from the next /
+//   previous row (edge class E / W; the cells on a wall column: no edge class).
+// Only the kinds matter: what lies outside the footprint cannot reach the owned cells within
+// T sweeps.  0 = none of this holds: tile kernel.
+__global__ void rb_class_kernel(const uint8_t *__restrict__ cflag, Geom g, int tiles_y, int BX,
+                                int BY, int h, uint8_t *__restrict__ cls) {
     const int tile = blockIdx.x;
     const int ti = tile / tiles_y, tj = tile - ti * tiles_y;
     const int64_t x0 = g.own0 + (int64_t)ti * BX;
     const int64_t x1 = min(x0 + BX, g.own1);
-    const int64_t col = (int64_t)tj * BY - h + threadIdx.x;
-    int ok = col >= 1 && col <= g.NY - 2;
+    int kind = IT_PLAIN;
+    int64_t c0 = (int64_t)tj * BY - h;
+    if (tj == 0) { kind = IT_WALL_LO; c0 = 0; }
+    else if (tj == tiles_y - 1) { kind = IT_WALL_HI; c0 = g.NY - SW; }
+    const int64_t col = c0 + threadIdx.x;
+    const bool wall_col = (kind == IT_WALL_LO && col == 0) || (kind == IT_WALL_HI && col == g.NY - 1);
+    int ok = tiles_y >= 2 && c0 >= 0 && (c0 & 1) == 0 && col < g.NY;
+    // the owned columns of the last tile column need h columns of strip to their left
+    if (kind == IT_WALL_HI && (int64_t)tj * BY - c0 < h) ok = 0;
+    if (kind == IT_PLAIN && (col < 1 || col > g.NY - 2)) ok = 0;
+    int bc_lo = 0, bc_hi = 0;
     if (ok) {
         for (int64_t r = x0 - h; r < x1 + h; r++) {
             const int64_t gx = g.gx0 + r;
-            if (r < 0 || r >= g.nxl || gx < 1 || gx > g.NX - 2 ||
-                cflag[r * g.pitch + col] != CF_FLUID) {
-                ok = 0;
-                break;
-            }
+            if (gx < 0 || gx >= g.NX) continue;      // beyond the grid: nothing there
+            if (r < 0 || r >= g.nxl) { ok = 0; break; }  // beyond this slab's rows
+            const uint8_t f = cflag[r * g.pitch + col];
+            if (gx == 0 || gx == g.NX - 1) {
+                // a boundary row: must be owned by this tile and be fed from the row inside
+                const int want = gx == 0 ? SB_EDGE_E : SB_EDGE_W;
+                if (r < x0 || r >= x1 || !cf_is_boundary(f) ||
+                    cf_edge(f) != (wall_col ? SB_EDGE_NONE : want)) { ok = 0; break; }
+                if (gx == 0) bc_lo = 1; else bc_hi = 1;
+            } else if (wall_col) {
+                if (!cf_is_boundary(f) ||
+                    cf_edge(f) != (kind == IT_WALL_LO ? SB_EDGE_S : SB_EDGE_N)) { ok = 0; break; }
+            } else if (!cf_is_fluid(f)) { ok = 0; break; }
         }
     }
     ok = __syncthreads_and(ok);
-    if (threadIdx.x == 0) plain[tile] = (uint8_t)ok;
+    if (threadIdx.x == 0)
+        cls[tile] = ok ? (uint8_t)(1 + kind + (bc_lo ? TC_BC_LO : 0) + (bc_hi ? TC_BC_HI : 0)) : 0;
 }
 
 }  // namespace
 
+static void dump_trace(sb_sim *s) {
+    std::vector<unsigned long long> t(4096 * 4);
+    cudaStreamSynchronize(s->stream);
+    if (cudaMemcpyFromSymbol(t.data(), g_trace, t.size() * 8) != cudaSuccess) return;
+    unsigned long long t0 = ~0ull;
+    const int n = std::min(s->plan.n_items, 4096);
+    for (int i = 0; i < n; i++)
+        if (t[4 * i + 1]) t0 = std::min(t0, t[4 * i]);
+    for (int i = 0; i < n; i++) {
+        if (!t[4 * i + 1]) continue;
+        fprintf(stderr, "[sb trace] item %d kind %d flags %d rows %d sm %d start %.1f us dur %.1f us\n",
+                i, (int)(t[4 * i + 3] & 3), (int)(t[4 * i + 3] & 0xff), (int)(t[4 * i + 3] >> 8),
+                (int)t[4 * i + 2], (t[4 * i] - t0) * 1e-3, (t[4 * i + 1] - t[4 * i]) * 1e-3);
+    }
+}
+
 void rb_plan_release(sb_sim *s) {
+    if (getenv("SB_STREAM_TRACE") && s->plan.n_items) dump_trace(s);
     cudaFree(s->plan.d_slow);
     cudaFree(s->plan.d_items);
     cudaFree(s->plan.d_plain);
@@ -425,21 +613,33 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
     if ((size_t)ntiles > pl.cap_tiles) {
         if (pl.d_slow) SB_CUDA(cudaFreeAsync(pl.d_slow, s->stream));
         if (pl.d_plain) SB_CUDA(cudaFreeAsync(pl.d_plain, s->stream));
-        if (pl.d_items) SB_CUDA(cudaFreeAsync(pl.d_items, s->stream));
-        pl.d_slow = nullptr; pl.d_plain = nullptr; pl.d_items = nullptr;
+        pl.d_slow = nullptr; pl.d_plain = nullptr;
         pl.cap_tiles = 0;
         SB_CUDA(cudaMallocAsync(&pl.d_slow, (size_t)ntiles * sizeof(int32_t), s->stream));
         SB_CUDA(cudaMallocAsync(&pl.d_plain, (size_t)ntiles, s->stream));
-        SB_CUDA(cudaMallocAsync(&pl.d_items, (size_t)ntiles * sizeof(RbItem), s->stream));
         pl.cap_tiles = (size_t)ntiles;
     }
-    rb_plain_kernel<<<ntiles, SW, 0, s->stream>>>(s->cflag, g, tiles_y, BX, BY, h, pl.d_plain);
+    rb_class_kernel<<<ntiles, SW, 0, s->stream>>>(s->cflag, g, tiles_y, BX, BY, h, pl.d_plain);
     s->launches++;
     SB_CUDA(cudaGetLastError());
-    std::vector<uint8_t> plain((size_t)ntiles);
-    SB_CUDA(cudaMemcpyAsync(plain.data(), pl.d_plain, (size_t)ntiles, cudaMemcpyDeviceToHost,
+    std::vector<uint8_t> cls((size_t)ntiles);
+    SB_CUDA(cudaMemcpyAsync(cls.data(), pl.d_plain, (size_t)ntiles, cudaMemcpyDeviceToHost,
                             s->stream));
     SB_CUDA(cudaStreamSynchronize(s->stream));
+    {
+        // Which kinds the streaming kernel takes: bit 0 wall strips, bit 1 tiles with boundary
+        // rows.  Wall strips run their own copy of the unrolled window; with T = 4 the three
+        // copies (48 + 53 + 53 KB) no longer fit the instruction caches the SMs share and the
+        // wall CTAs (and some of their neighbours) run 1.5-2x slower than the rest, which
+        // costs more than the tile-kernel launch they save (profiles/r1_stream_kinds_ab.txt);
+        // up to T = 3 (32 + 36 + 36 KB) they pay off.  SB_RB_STREAM_KINDS overrides (A/B runs).
+        int keep = T <= 3 ? 3 : 2;
+        if (const char *e = getenv("SB_RB_STREAM_KINDS")) keep = atoi(e);
+        for (auto &c : cls) {
+            if (!(keep & 1) && (c & 3) != 1 + IT_PLAIN) c = 0;
+            if (!(keep & 2) && (c & (TC_BC_LO | TC_BC_HI))) c = 0;
+        }
+    }
     if (s->slab) {
         // tiles that own rows within H of a slab edge also feed the neighbour's halo rows:
         // that code lives in the tile kernel
@@ -449,72 +649,113 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
             const bool lo = s->link.lo_p[0] != nullptr && x0 < g.own0 + H;
             const bool hi = s->link.hi_p[0] != nullptr && x1 > g.own1 - H;
             if (lo || hi)
-                for (int tj = 0; tj < tiles_y; tj++) plain[(size_t)ti * tiles_y + tj] = 0;
+                for (int tj = 0; tj < tiles_y; tj++) cls[(size_t)ti * tiles_y + tj] = 0;
         }
     }
-    // runs of plain tiles along x, per strip
-    struct Run { int tj, ti0, len; };
+    // runs of tiles of one item kind along x, per strip.  weight: how much longer a wall
+    // strip takes per row than a plain one; its items get that much fewer rows
+    struct Run { int tj, ti0, len, kind; double weight; };
+    double wall_weight = 2.0;  // measured: wall items run ~1.5-2x slower per row (see above)
+    if (const char *e = getenv("SB_WALL_WEIGHT")) wall_weight = atof(e);
     std::vector<Run> runs;
     std::vector<int32_t> slow;
     for (int tj = 0; tj < tiles_y; tj++) {
         int ti = 0;
         while (ti < tiles_x) {
-            if (!plain[(size_t)ti * tiles_y + tj]) { ti++; continue; }
+            const int k = cls[(size_t)ti * tiles_y + tj] & 3;
+            if (!k) { ti++; continue; }
             int t0 = ti;
-            while (ti < tiles_x && plain[(size_t)ti * tiles_y + tj]) ti++;
-            runs.push_back({tj, t0, ti - t0});
+            while (ti < tiles_x && (cls[(size_t)ti * tiles_y + tj] & 3) == k) ti++;
+            runs.push_back({tj, t0, ti - t0, k - 1, k - 1 == IT_PLAIN ? 1.0 : wall_weight});
         }
     }
     for (int t = 0; t < ntiles; t++)
-        if (!plain[(size_t)t]) slow.push_back(t);
-    // tiles per item: as many items as keep every SM's warps busy in whole waves, as long as
-    // possible otherwise (every item pays 2(2T+2) warm-up rows)
-    static bool carveout_set = false;
-    if (!carveout_set) {
-        for (int tb = 1; tb <= RB_TMAX; tb++)
-            cudaFuncSetAttribute(stream_kernel(tb), cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
-        carveout_set = true;
+        if (!cls[(size_t)t]) slow.push_back(t);
+    // Tiles per item: as many items as fill the SMs in whole waves of CTAs, as long as
+    // possible otherwise (every open end of an item pays 2T+2 warm-up rows).  A CTA holds
+    // `nwarp` items of ONE kind.
+    const int nwarp = stream_cta_warps(T);
+    {
+        // per device: the attributes live with the function in each context
+        static bool attrs_set[64] = {false};
+        const int dev = s->device & 63;
+        if (!attrs_set[dev]) {
+            for (int tb = 1; tb <= RB_TMAX; tb++) {
+                cudaFuncSetAttribute(stream_kernel(tb),
+                                     cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared);
+                cudaFuncSetAttribute(stream_kernel(tb), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     stream_smem_bytes(tb));
+            }
+            attrs_set[dev] = true;
+        }
     }
-    int dev_sms = 148, ctas = 8;
+    int dev_sms = 148, ctas = 1;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, s->device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, stream_kernel(T), 32,
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, stream_kernel(T), 32 * nwarp,
                                                   stream_smem_bytes(T));
     if (ctas < 1) ctas = 1;
-    const int64_t resident = (int64_t)dev_sms * ctas;
+    const int64_t resident = (int64_t)dev_sms * ctas;  // CTAs at a time
+    auto pieces = [](const Run &r, int seg) {
+        return std::max(1, std::min(r.len, (int)((r.len * r.weight + seg - 1) / seg)));
+    };
     int best_seg = 1;
     double best_cost = 1e300;
     for (int seg = 1; seg <= 256; seg++) {
-        int64_t n = 0;
-        int longest = 0;
+        int64_t n[3] = {0, 0, 0};
+        double longest = 0;
         for (const Run &r : runs) {
-            const int m = (r.len + seg - 1) / seg;
-            n += m;
-            longest = std::max(longest, (r.len + m - 1) / m);
+            const int m = pieces(r, seg);
+            n[r.kind] += m;
+            longest = std::max(longest, ((r.len + m - 1) / m) * r.weight);
         }
-        if (n == 0) break;
-        const int64_t waves = (n + resident - 1) / resident;
-        const double cost = (double)waves * ((double)longest * BX + 2.0 * h);
+        const int64_t nc = (n[0] + nwarp - 1) / nwarp + (n[1] + nwarp - 1) / nwarp +
+                           (n[2] + nwarp - 1) / nwarp;
+        if (nc == 0) break;
+        const int64_t waves = (nc + resident - 1) / resident;
+        const double cost = (double)waves * (longest * BX + 2.0 * h);
         if (cost < best_cost) { best_cost = cost; best_seg = seg; }
     }
-    std::vector<RbItem> items;
+    std::vector<RbItem> by_kind[3];
     for (const Run &r : runs) {
-        const int m = (r.len + best_seg - 1) / best_seg;
+        const int m = pieces(r, best_seg);
         for (int i = 0; i < m; i++) {
             const int a = (int)((int64_t)r.len * i / m), b = (int)((int64_t)r.len * (i + 1) / m);
             RbItem it;
             it.x0 = (int32_t)(g.own0 + (int64_t)(r.ti0 + a) * BX);
             it.x1 = (int32_t)std::min<int64_t>(g.own0 + (int64_t)(r.ti0 + b) * BX, g.own1);
+            int flags = r.kind, st0 = h, st1 = SW - h;
             it.ty0 = r.tj * BY - h;
-            it.pad = 0;
-            items.push_back(it);
+            if (r.kind == IT_WALL_LO) { it.ty0 = 0; st0 = 0; st1 = BY; }
+            if (r.kind == IT_WALL_HI) {
+                it.ty0 = (int32_t)(g.NY - SW);
+                st0 = r.tj * BY - it.ty0;
+                st1 = SW;
+            }
+            if (cls[(size_t)(r.ti0 + a) * tiles_y + r.tj] & TC_BC_LO) flags |= IT_BC_LO;
+            if (cls[(size_t)(r.ti0 + b - 1) * tiles_y + r.tj] & TC_BC_HI) flags |= IT_BC_HI;
+            it.pad = flags | (st0 << 8) | (st1 << 16);
+            by_kind[r.kind].push_back(it);
         }
     }
-    // neighbouring strips of the same rows run side by side: their shared halo columns are
-    // then fetched from HBM once
-    std::stable_sort(items.begin(), items.end(), [](const RbItem &a, const RbItem &b) {
-        return a.x0 != b.x0 ? a.x0 < b.x0 : a.ty0 < b.ty0;
-    });
+    // kind by kind, each padded to whole CTAs; inside a kind neighbouring strips of the same
+    // rows run side by side: their shared halo columns are then fetched from HBM once
+    std::vector<RbItem> items;
+    for (auto &v : by_kind) {
+        std::stable_sort(v.begin(), v.end(), [](const RbItem &a, const RbItem &b) {
+            return a.x0 != b.x0 ? a.x0 < b.x0 : a.ty0 < b.ty0;
+        });
+        items.insert(items.end(), v.begin(), v.end());
+        while (items.size() % nwarp) items.push_back(RbItem{0, 0, 0, 0});
+    }
+    if (getenv("SB_STREAM_REVERSE")) std::reverse(items.begin(), items.end());  // experiment
+    if (items.size() > pl.cap_items) {
+        if (pl.d_items) SB_CUDA(cudaFreeAsync(pl.d_items, s->stream));
+        pl.d_items = nullptr;
+        pl.cap_items = 0;
+        SB_CUDA(cudaMallocAsync(&pl.d_items, items.size() * sizeof(RbItem), s->stream));
+        pl.cap_items = items.size();
+    }
     if (!slow.empty())
         SB_CUDA(cudaMemcpyAsync(pl.d_slow, slow.data(), slow.size() * sizeof(int32_t),
                                 cudaMemcpyHostToDevice, s->stream));
@@ -522,6 +763,19 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
         SB_CUDA(cudaMemcpyAsync(pl.d_items, items.data(), items.size() * sizeof(RbItem),
                                 cudaMemcpyHostToDevice, s->stream));
     SB_CUDA(cudaStreamSynchronize(s->stream));  // the vectors go out of scope
+    if (getenv("SB_DEBUG_PLAN")) {
+        int nk[3] = {0, 0, 0}, nbc = 0, longest = 0;
+        for (const RbItem &it : items) {
+            if (it.x1 <= it.x0) continue;
+            nk[it.pad & 3]++;
+            nbc += (it.pad & (IT_BC_LO | IT_BC_HI)) != 0;
+            longest = std::max(longest, it.x1 - it.x0);
+        }
+        fprintf(stderr, "[sb plan] T=%d tiles %dx%d slow %zu items %zu (plain %d, wall %d+%d, with "
+                "boundary rows %d) longest %d rows, seg %d, resident CTAs %lld\n", T, tiles_x,
+                tiles_y, slow.size(), items.size(), nk[0], nk[1], nk[2], nbc, longest, best_seg,
+                (long long)resident);
+    }
     pl.n_slow = (int)slow.size();
     pl.n_items = (int)items.size();
     pl.tiles_x = tiles_x;
@@ -535,9 +789,16 @@ sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h)
     const Geom &g = s->g;
     const int gpar = (int)(((g.gx0 % 2) + 2) % 2);
     const int TB = s->prm.temporal_block;
-    stream_kernel(TB)<<<s->plan.n_items, 32, stream_smem_bytes(TB), s->stream>>>(
+    const int nw = stream_cta_warps(TB);
+    static int trace_set = 0;
+    if (!trace_set && getenv("SB_STREAM_TRACE")) {
+        const int one = 1;
+        cudaMemcpyToSymbol(g_trace_on, &one, sizeof(int));
+        trace_set = 1;
+    }
+    stream_kernel(TB)<<<s->plan.n_items / nw, 32 * nw, stream_smem_bytes(TB), s->stream>>>(
         s->plan.d_items, rb_pbuf_ptr(s), s->rhs, s->d_ctl, s->d_partial, part_base, part_stride,
-        g.pitch, gpar, h, rb_consts(s));
+        g.pitch, gpar, rb_consts(s));
     s->launches++;
     SB_CUDA(cudaGetLastError());
     return SB_OK;
@@ -546,7 +807,7 @@ sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h)
 void preload_sor_rb_stream() {
     cudaFuncAttributes a;
     for (int tb = 1; tb <= RB_TMAX; tb++) cudaFuncGetAttributes(&a, stream_kernel(tb));
-    cudaFuncGetAttributes(&a, rb_plain_kernel);
+    cudaFuncGetAttributes(&a, rb_class_kernel);
     cudaGetLastError();
 }
 

@@ -335,7 +335,6 @@ class Simulation:
     def kernel_launches(self):
         return int(_capi.lib().sb_kernel_launches(self._h))
 
-    @property
     def render_simulation(self, color_type="pressure"):
         """render_simulation (src/visualization.rs:79-105) on the device: the RGBA8 frame in
         macroquad's Image layout, shape (ny, owned rows, 4) -- image[y, x] is the pixel of
@@ -345,6 +344,7 @@ class Simulation:
         self._check(_capi.lib().sb_render_rgba(self._h, ct, img.ctypes.data))
         return img
 
+    @property
     def rb_plan(self):
         """(tiles on the tile kernel, work items of the streaming kernel) of the last pass"""
         a, b = C.c_int32(), C.c_int32()
