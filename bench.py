@@ -43,12 +43,18 @@ METRIC = "Mcell-steps/s (full step incl. SOR)"
 UNIT = "Mcell-steps/s"
 SOR_BYTES_PER_CELL_SWEEP = 25.0   # read p, rhs, flag; write p
 TICK_FIXED_BYTES_PER_CELL = 81.0  # F/G+RHS 40 + velocity update/ranges 41
-# dram__bytes_read.sum + dram__bytes_write.sum per sor_rb_kernel launch, from the committed
-# `ncu --set full` capture (profiles/); None until a capture for this configuration exists
-NCU_TRAFFIC_BYTES = {
-    # profiles/r1_sor_rb_T2_8192_ncu_full.txt (algorithmic: 25 B x 8192^2 = 1 677 721 600)
-    "rb-T2-8192x8192": 1650447464,
-}
+# dram__bytes_read.sum + dram__bytes_write.sum per SOR pass (the streaming kernel plus the
+# tile kernel on what is left), from the committed `ncu --set full` captures: see
+# profiles/ncu_traffic.json (key "<mode>-T<T>-<rows>x<ny>"); None until a capture exists
+
+
+def ncu_traffic(key):
+    f = ROOT / "profiles" / "ncu_traffic.json"
+    if not f.exists():
+        return None
+    e = json.loads(f.read_text()).get(key)
+    return e["bytes_per_pass"] if e else None
+
 
 
 def workload(name, n_gpus, size=None):
@@ -327,7 +333,7 @@ def run_ours(args):
 
     # -- roofline of the dominant kernel (the SOR pass) -------------------------------------
     peak, peak_src = measured_peak_gbs()
-    T = sim.temporal_block if args.mode == "rb" else 1
+    T = (sim.temporal_block or 4) if args.mode == "rb" else 1  # 0 = the library default (4)
     work = [m for m in pass_ms if m > 0.2 * (max(pass_ms) if len(pass_ms) else 1.0)]
     local_cells = rows * ny
     roof = None
@@ -337,14 +343,21 @@ def run_ours(args):
         alg_bytes = SOR_BYTES_PER_CELL_SWEEP * local_cells * sweeps_per_launch
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
         key = f"{args.mode}-T{T}-{rows}x{ny}"
-        roof = {"bound": "hbm", "kernel": "sor_rb_kernel" if args.mode == "rb" else "sor_lex_kernel",
+        traffic = ncu_traffic(key)
+        roof = {"bound": "hbm",
+                "kernel": (f"SOR pass = sor_rb_stream_kernel<{T}> on {rb_plan[1]} work items + "
+                           f"sor_rb_kernel on {rb_plan[0]} tiles") if args.mode == "rb"
+                else "sor_lex_kernel",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC_BYTES.get(key),
+                "traffic": traffic,
+                "dram_gbs": traffic / (avg_ms * 1e-3) / 1e9 if traffic else None,
                 "peak_source": peak_src, "launches_timed": len(work),
                 "avg_launch_ms": avg_ms, "sweeps_per_launch": sweeps_per_launch,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "25 B per cell-sweep x cells x sweeps per launch; CUDA events around "
-                        "every launch of the timed region"}
+                "note": "achieved = 25 B per cell-sweep x cells x sweeps per pass / pass time "
+                        "(CUDA events around every pass of the timed region); a pass fuses T "
+                        "sweeps, so it moves ~25 B per cell once (traffic, dram_gbs) and the "
+                        "algorithmic figure may exceed the HBM peak"}
     barrier()
     sim.close()
     if rank != 0:

@@ -92,13 +92,13 @@ __host__ __device__ constexpr int stream_warps(int TB) {
     return TB == 1 ? 16 : TB <= 3 ? 12 : 8;
 }
 // All warps of an SM form ONE CTA (they never synchronise with each other) whose items are
-// all of the same kind.  The unrolled window of one kind is 32 KB (T = 3) to 50 KB (T = 4) of
-// code against 32 KB of L1.5 instruction cache per SM: warps of different kinds on one SM
-// evict each other's loop -- measured (profiles/r1_stream_kinds_ab.txt) a pass with 3 % of
-// wall items scattered over the SMs takes 0.63 ms, the same items all on one code path 0.43.
+// all of the same kind (plain / wall strip), so an SM runs one copy of the unrolled window:
+// it is 32 KB (T = 3) to 50 KB (T = 4) of code against 32 KB of L1.5 instruction cache.
+// Against one-warp CTAs this alone gains 8 % at T = 4 (profiles/r1_stream_kinds_ab.txt).
 
 // SB_STREAM_TRACE=1: per item of the last pass: start, end (globaltimer ns), SM, kind
 __device__ unsigned long long g_trace[4096 * 4];
+__device__ unsigned long long g_trace2[4096 * 2];  // first entry into / last exit from the steady loop
 __device__ int g_trace_on;
 __device__ __forceinline__ unsigned long long gtime() {
     unsigned long long t;
@@ -125,6 +125,7 @@ struct SCtx {
     int bc_lo, bc_hi;          // boundary rows of the item (far out of range if none)
     int first, re;             // rows loaded: [first, re)
     int rend;                  // ticks run for rows [rs, rend): rend = x1 + 2T+2 (drain)
+    int trace_idx;             // SB_STREAM_TRACE: slot of this item, -1 = none
     int lane, lane_m1, lane_p1;
     bool cmA, cmB;             // the pair lies in the strip's stored / counted columns
     bool keepA, keepB;         // A0 / B1 of this lane is a wall cell
@@ -181,10 +182,12 @@ __device__ __forceinline__ void half_sweep(double (&W)[2 * T + 4][4], const int 
     constexpr int NW = stream_nw(T);
     constexpr int ia = SET, ib = SET + 2, oa = SET ^ 1, ob = (SET ^ 1) + 2;
     // the wall cell is one of these cells / the fluid cell next to the wall is
-    constexpr bool wall_a = WALL == IT_WALL_LO && SET == 0;   // cell 0 of lane 0
-    constexpr bool wall_b = WALL == IT_WALL_HI && SET == 1;   // cell 3 of lane 31
-    constexpr bool adj_a = WALL == IT_WALL_LO && SET == 1;    // cell 1 of lane 0
-    constexpr bool adj_b = WALL == IT_WALL_HI && SET == 0;    // cell 2 of lane 31
+    // WALL: the strip has a wall column -- cell 0 of lane 0 (keepA) or cell 3 of lane 31
+    // (keepB), told apart at run time so that both share one copy of the code
+    constexpr bool wall_a = WALL && SET == 0;   // cell 0 may be the wall cell
+    constexpr bool wall_b = WALL && SET == 1;   // cell 3 may be the wall cell
+    constexpr bool adj_a = WALL && SET == 1;    // cell 1 may be the fluid cell next to it
+    constexpr bool adj_b = WALL && SET == 0;    // cell 2 may be
     const RbConsts &k = c.k;
     const int sm = (s + NW - 1) % NW, sp = (s + 1) % NW;
     if (!STEADY && (q == c.bc_lo || q == c.bc_hi)) return;   // a boundary row: not swept
@@ -195,28 +198,29 @@ __device__ __forceinline__ void half_sweep(double (&W)[2 * T + 4][4], const int 
     const bool row_lo = !STEADY && RED && q == c.bc_lo + 1;
     const bool row_hi = !STEADY && RED && q == c.bc_hi - 1;
     auto refresh_wall = [&]() {
-        if (WALL == IT_WALL_LO) W[s][0] = c.keepA ? W[s][1] : W[s][0];
-        if (WALL == IT_WALL_HI) W[s][3] = c.keepB ? W[s][2] : W[s][3];
+        if (WALL) {
+            W[s][0] = c.keepA ? W[s][1] : W[s][0];
+            W[s][3] = c.keepB ? W[s][2] : W[s][3];
+        }
     };
     auto refresh_rows = [&]() {
         if (row_lo) {
-            W[sm][0] = (WALL == IT_WALL_LO && c.keepA) ? W[sm][0] : W[s][0];
+            W[sm][0] = (WALL && c.keepA) ? W[sm][0] : W[s][0];
             W[sm][1] = W[s][1];
             W[sm][2] = W[s][2];
-            W[sm][3] = (WALL == IT_WALL_HI && c.keepB) ? W[sm][3] : W[s][3];
+            W[sm][3] = (WALL && c.keepB) ? W[sm][3] : W[s][3];
         }
         if (row_hi) {
-            W[sp][0] = (WALL == IT_WALL_LO && c.keepA) ? W[sp][0] : W[s][0];
+            W[sp][0] = (WALL && c.keepA) ? W[sp][0] : W[s][0];
             W[sp][1] = W[s][1];
             W[sp][2] = W[s][2];
-            W[sp][3] = (WALL == IT_WALL_HI && c.keepB) ? W[sp][3] : W[s][3];
+            W[sp][3] = (WALL && c.keepB) ? W[sp][3] : W[s][3];
         }
     };
     if (RED && !late) {  // first sweep of the pass: nothing is late, refresh first
         refresh_wall();
         if (!STEADY) refresh_rows();
     }
-    if (RED && late && !(adj_a || adj_b)) refresh_wall();  // no counted cell sees the wall here
     double na, nb;
     nbr2<SET>(c, W[s], na, nb);
     double xa = W[sp][ia] + W[sm][ia], xb = W[sp][ib] + W[sm][ib];
@@ -333,14 +337,14 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
                          tsum(k, W[sp][0] + W[sm][0], W[s][1] + na, FR[U & 1][0]));
                 rb = fma(-k.diag, W[s][2],
                          tsum(k, W[sp][2] + W[sm][2], W[s][3] + nb, FR[U & 1][1]));
-                if (WALL == IT_WALL_LO) ra = c.keepA ? 0.0 : ra;
+                if (WALL) ra = c.keepA ? 0.0 : ra;
             } else {
                 nbr2<1>(c, W[s], na, nb);
                 ra = fma(-k.diag, W[s][1],
                          tsum(k, W[sp][1] + W[sm][1], W[s][0] + na, FR[U & 1][0]));
                 rb = fma(-k.diag, W[s][3],
                          tsum(k, W[sp][3] + W[sm][3], W[s][2] + nb, FR[U & 1][1]));
-                if (WALL == IT_WALL_HI) rb = c.keepB ? 0.0 : rb;
+                if (WALL) rb = c.keepB ? 0.0 : rb;
             }
             accA[T - 1] = fma(ra, ra, accA[T - 1]);
             accB[T - 1] = fma(rb, rb, accB[T - 1]);
@@ -374,8 +378,8 @@ __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
     c.bc_hi = hi ? c.x1 - 1 : (1 << 29);
     c.cx0 = c.x0 + (lo ? 1 : 0);
     c.cx1 = c.x1 - (hi ? 1 : 0);
-    c.keepA = WALL == IT_WALL_LO && c.lane == 0;
-    c.keepB = WALL == IT_WALL_HI && c.lane == 31;
+    c.keepA = (flags & 3) == IT_WALL_LO && c.lane == 0;
+    c.keepB = (flags & 3) == IT_WALL_HI && c.lane == 31;
     // the tick loop starts on a row of even global x so that register slot parity = row parity
     const int rs = c.first - ((gpar + c.first) & 1);
     // steady ticks R in [st_lo, st_hi]: rows R-1 .. R-(2T+2) are ordinary counted rows (not
@@ -400,6 +404,8 @@ __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
     int64_t roff = (int64_t)rs * c.pitch;
     for (int R0 = rs; R0 < c.rend;) {
         if (R0 >= st_lo && R0 + NW - 1 <= st_hi) {
+            if (g_trace_on && c.lane == 0 && c.trace_idx >= 0 && !g_trace2[2 * c.trace_idx])
+                g_trace2[2 * c.trace_idx] = gtime();
             do {  // the steady state: straight-line code, no row tests
 #pragma unroll
                 for (int U = 0; U < NW; U++) {
@@ -409,6 +415,8 @@ __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
                 ph ^= 1u;
                 R0 += NW;
             } while (R0 + NW - 1 <= st_hi);
+            if (g_trace_on && c.lane == 0 && c.trace_idx >= 0)
+                g_trace2[2 * c.trace_idx + 1] = gtime();
         } else {
 #pragma unroll
             for (int U = 0; U < NW; U++) {
@@ -430,10 +438,8 @@ __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
 template <int T>
 __device__ __forceinline__ void stream_item_any(SCtx &c, int flags, int gpar, double *partial,
                                                 int64_t part_stride) {
-    const int wall = flags & 3;
-    if (wall == IT_PLAIN) stream_item<T, IT_PLAIN>(c, flags, gpar, partial, part_stride);
-    else if (wall == IT_WALL_LO) stream_item<T, IT_WALL_LO>(c, flags, gpar, partial, part_stride);
-    else stream_item<T, IT_WALL_HI>(c, flags, gpar, partial, part_stride);
+    if ((flags & 3) == IT_PLAIN) stream_item<T, 0>(c, flags, gpar, partial, part_stride);
+    else stream_item<T, 1>(c, flags, gpar, partial, part_stride);
 }
 
 // one work item per warp, stream_warps(TB) warps per CTA, one CTA per SM; TB = the configured
@@ -483,7 +489,9 @@ sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict
     c.cmA = 2 * c.lane >= st0 && 2 * c.lane < st1;
     c.cmB = 64 + 2 * c.lane >= st0 && 64 + 2 * c.lane < st1;
     const bool trace = g_trace_on && idx < 4096;
+    c.trace_idx = trace ? idx : -1;
     if (trace && c.lane == 0) {
+        g_trace2[2 * idx] = 0;
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         g_trace[4 * idx] = gtime();
@@ -577,18 +585,22 @@ __global__ void rb_class_kernel(const uint8_t *__restrict__ cflag, Geom g, int t
 }  // namespace
 
 static void dump_trace(sb_sim *s) {
-    std::vector<unsigned long long> t(4096 * 4);
+    std::vector<unsigned long long> t(4096 * 4), t2(4096 * 2);
     cudaStreamSynchronize(s->stream);
     if (cudaMemcpyFromSymbol(t.data(), g_trace, t.size() * 8) != cudaSuccess) return;
+    if (cudaMemcpyFromSymbol(t2.data(), g_trace2, t2.size() * 8) != cudaSuccess) return;
     unsigned long long t0 = ~0ull;
     const int n = std::min(s->plan.n_items, 4096);
     for (int i = 0; i < n; i++)
         if (t[4 * i + 1]) t0 = std::min(t0, t[4 * i]);
     for (int i = 0; i < n; i++) {
         if (!t[4 * i + 1]) continue;
-        fprintf(stderr, "[sb trace] item %d kind %d flags %d rows %d sm %d start %.1f us dur %.1f us\n",
+        fprintf(stderr, "[sb trace] item %d kind %d flags %d rows %d sm %d start %.1f us dur %.1f us"
+                " warmup %.1f steady %.1f drain %.1f\n",
                 i, (int)(t[4 * i + 3] & 3), (int)(t[4 * i + 3] & 0xff), (int)(t[4 * i + 3] >> 8),
-                (int)t[4 * i + 2], (t[4 * i] - t0) * 1e-3, (t[4 * i + 1] - t[4 * i]) * 1e-3);
+                (int)t[4 * i + 2], (t[4 * i] - t0) * 1e-3, (t[4 * i + 1] - t[4 * i]) * 1e-3,
+                (t2[2 * i] - t[4 * i]) * 1e-3, (t2[2 * i + 1] - t2[2 * i]) * 1e-3,
+                (t[4 * i + 1] - t2[2 * i + 1]) * 1e-3);
     }
 }
 
@@ -628,11 +640,11 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
     SB_CUDA(cudaStreamSynchronize(s->stream));
     {
         // Which kinds the streaming kernel takes: bit 0 wall strips, bit 1 tiles with boundary
-        // rows.  Wall strips run their own copy of the unrolled window; with T = 4 the three
-        // copies (48 + 53 + 53 KB) no longer fit the instruction caches the SMs share and the
-        // wall CTAs (and some of their neighbours) run 1.5-2x slower than the rest, which
-        // costs more than the tile-kernel launch they save (profiles/r1_stream_kinds_ab.txt);
-        // up to T = 3 (32 + 36 + 36 KB) they pay off.  SB_RB_STREAM_KINDS overrides (A/B runs).
+        // rows.  The wall copy of the window costs 0.81 us per row-tick against 0.51 for the
+        // plain one at T = 4 (per-item trace, profiles/r1_stream_kinds_ab.txt): its items get
+        // half the rows (wall_weight) and fill ~8 SMs, which on a wide grid only breaks even
+        // with leaving the wall tiles to the tile kernel; up to T = 3 it wins (0.343 vs
+        // 0.394 ms per pass at 8192^2).  SB_RB_STREAM_KINDS overrides (A/B runs).
         int keep = T <= 3 ? 3 : 2;
         if (const char *e = getenv("SB_RB_STREAM_KINDS")) keep = atoi(e);
         for (auto &c : cls) {
@@ -702,21 +714,20 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
     int best_seg = 1;
     double best_cost = 1e300;
     for (int seg = 1; seg <= 256; seg++) {
-        int64_t n[3] = {0, 0, 0};
+        int64_t n[2] = {0, 0};
         double longest = 0;
         for (const Run &r : runs) {
             const int m = pieces(r, seg);
-            n[r.kind] += m;
+            n[r.kind != IT_PLAIN] += m;
             longest = std::max(longest, ((r.len + m - 1) / m) * r.weight);
         }
-        const int64_t nc = (n[0] + nwarp - 1) / nwarp + (n[1] + nwarp - 1) / nwarp +
-                           (n[2] + nwarp - 1) / nwarp;
+        const int64_t nc = (n[0] + nwarp - 1) / nwarp + (n[1] + nwarp - 1) / nwarp;
         if (nc == 0) break;
         const int64_t waves = (nc + resident - 1) / resident;
         const double cost = (double)waves * (longest * BX + 2.0 * h);
         if (cost < best_cost) { best_cost = cost; best_seg = seg; }
     }
-    std::vector<RbItem> by_kind[3];
+    std::vector<RbItem> by_kind[2];  // plain strips / wall strips: one copy of the code each
     for (const Run &r : runs) {
         const int m = pieces(r, best_seg);
         for (int i = 0; i < m; i++) {
@@ -735,7 +746,7 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
             if (cls[(size_t)(r.ti0 + a) * tiles_y + r.tj] & TC_BC_LO) flags |= IT_BC_LO;
             if (cls[(size_t)(r.ti0 + b - 1) * tiles_y + r.tj] & TC_BC_HI) flags |= IT_BC_HI;
             it.pad = flags | (st0 << 8) | (st1 << 16);
-            by_kind[r.kind].push_back(it);
+            by_kind[r.kind != IT_PLAIN].push_back(it);
         }
     }
     // kind by kind, each padded to whole CTAs; inside a kind neighbouring strips of the same
@@ -748,7 +759,6 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
         items.insert(items.end(), v.begin(), v.end());
         while (items.size() % nwarp) items.push_back(RbItem{0, 0, 0, 0});
     }
-    if (getenv("SB_STREAM_REVERSE")) std::reverse(items.begin(), items.end());  // experiment
     if (items.size() > pl.cap_items) {
         if (pl.d_items) SB_CUDA(cudaFreeAsync(pl.d_items, s->stream));
         pl.d_items = nullptr;
