@@ -24,13 +24,10 @@ like the Rust original) on a bounded sample of the same workload.
 """
 import argparse
 import ctypes as C
-import datetime
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import time
 from pathlib import Path
 
@@ -91,65 +88,71 @@ def workload(name, n_gpus, size=None):
 
 # ---- clocks ---------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line).
-
-    nvidia-smi needs ~0.5 s before its first sample, so the sampler is started ahead of the
-    warm-up; only the samples whose timestamp falls inside [begin(), end()] are reported."""
-    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons sampled DURING the timed region (the quantities of
+    the B200_PROFILING.md clocks line), read through NVML from a background thread every
+    ~5 ms -- the timed region of a 20-tick run is a fraction of a second, too short for
+    `nvidia-smi -lms`.  Only samples taken between begin() and end() are reported."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+               "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
-        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.proc = None
-        self.t0 = self.t1 = None
+        self.samples = []
+        self.active = False
+        self.stop_flag = False
+        self.thread = None
+        self.smax = None
+
+    def _loop(self, nv, h):
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    try:
+                        rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.samples.append((sm, pw, rs))
+                except Exception:
+                    pass
+            time.sleep(0.005)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "50", "-i", str(self.gpu_index)],
-                stdout=self.tmp, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+            import threading
+
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu_index
+            if vis:
+                idx = int(vis.split(",")[self.gpu_index])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._loop, args=(nv, h), daemon=True)
+            self.thread.start()
+        except Exception:
+            self.thread = None
 
     def begin(self):
-        self.t0 = datetime.datetime.now()
+        self.active = True
 
     def end(self):
-        self.t1 = datetime.datetime.now()
+        self.active = False
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": [], "samples": 0}
+        if self.thread is None:
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        self.tmp.flush()
-        rows = [r.split(",") for r in Path(self.tmp.name).read_text().splitlines() if r.strip()]
-        os.unlink(self.tmp.name)
-        sm, smax, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f")
-                if self.t0 and self.t1 and not (self.t0 <= ts <= self.t1):
-                    continue
-                sm.append(float(r[1]))
-                smax.append(float(r[2]))
-                power.append(float(r[3]))
-            except (ValueError, IndexError):
-                continue
-            for name, val in zip(names, r[5:9]):
-                if val.strip().lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), samples=len(sm),
-                       power_w_max=max(power), reasons=sorted(reasons))
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        if self.samples:
+            reasons = sorted(name for name, bit in self.REASONS.items()
+                             if any(r & bit for _, _, r in self.samples))
+            out.update(sm_mhz=statistics.median(x[0] for x in self.samples),
+                       samples=len(self.samples), reasons=reasons,
+                       power_w_max=max(x[1] for x in self.samples))
         return out
 
 
