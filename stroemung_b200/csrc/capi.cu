@@ -251,8 +251,10 @@ static void adapt_delt(sb_sim *s) {
 }
 
 // solve_sor (src/simulation.rs:239-285).  test_exit = 0: exactly max_it sweeps.
+// cap_hit_out != nullptr: the caller takes over grid.calculate_pressure_range() after a capped
+// solve (the tick fuses it into the velocity update) and gets told whether it is due
 static sb_status solve(sb_sim *s, uint32_t max_it, int test_exit, uint32_t *iters, double *norm,
-                       double *norm_hist_host) {
+                       double *norm_hist_host, int *cap_hit_out = nullptr) {
     sb_status st;
     const bool rb = is_rb(s);
     const int T = rb ? s->prm.temporal_block : 1;
@@ -340,7 +342,8 @@ static sb_status solve(sb_sim *s, uint32_t max_it, int test_exit, uint32_t *iter
     int cap_hit = h->cap_hit;
     if ((st = sync_ctl_idle(s))) return st;
     // grid.calculate_pressure_range() only when the cap is hit (src/simulation.rs:283)
-    if (cap_hit && test_exit)
+    if (cap_hit_out) *cap_hit_out = cap_hit && test_exit;
+    else if (cap_hit && test_exit)
         if ((st = launch_pressure_range(s))) return st;
     return SB_OK;
 }
@@ -350,8 +353,9 @@ static sb_status tick(sb_sim *s, uint32_t *iters, double *norm) {
     if (s->prm.tau > 0.0) adapt_delt(s);
     if ((st = launch_velocity_bc(s))) return st;
     if ((st = launch_fg_rhs(s, 3))) return st;
-    if ((st = solve(s, s->prm.max_iterations, 1, iters, norm, nullptr))) return st;
-    if ((st = launch_adapt_uv(s))) return st;
+    int prange_due = 0;
+    if ((st = solve(s, s->prm.max_iterations, 1, iters, norm, nullptr, &prange_due))) return st;
+    if ((st = launch_adapt_uv(s, prange_due))) return st;
     s->time += s->prm.delt;
     s->iterations += 1;
     s->last_sor_iterations = *iters;

@@ -52,21 +52,25 @@ struct DivC {
 // The same correction steps without a branch per division: the operand check (exponent
 // inside the safe window, or an exact zero) is accumulated into *bad with integer
 // instructions and the caller redoes the whole cell with plain divisions if it ever fires.
-// The sign of a zero quotient is taken from q0 = a*r (the fma chain would give +0 for -0).
 struct DivF {
     double d, r;
     unsigned *bad;
     __device__ __forceinline__ double operator()(double a) const {
-        const int hi = __double2hiint(a);
-        const unsigned e = ((unsigned)hi >> 20) & 0x7ffu;
-        const bool ok = (e - 573u) <= 900u || (((unsigned)hi << 1) | (unsigned)__double2loint(a)) == 0u;
-        *bad |= ok ? 0u : 1u;
+        // operand check on the high word: exponent field in [573, 1473] (2^-450 .. 2^450),
+        // or an exact zero
+        const unsigned hi = (unsigned)__double2hiint(a);
+        const unsigned ha = hi & 0x7fffffffu;
+        const bool inwin = (ha - (573u << 20)) < (901u << 20);
+        const bool zero = (ha | (unsigned)__double2loint(a)) == 0u;
+        *bad |= (inwin || zero) ? 0u : 1u;
         const double q0 = a * r;
         double er = fma(-d, q0, a);
         double q = fma(er, r, q0);
         er = fma(-d, q, a);
         q = fma(er, r, q);
-        return q == 0.0 ? q0 : q;
+        // sign from q0 = a*r: right for every quotient, and the fma chain would turn -0 into +0
+        return __hiloint2double((__double2hiint(q) & 0x7fffffff) | (__double2hiint(q0) & 0x80000000),
+                                __double2loint(q));
     }
 };
 

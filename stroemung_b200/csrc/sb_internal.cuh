@@ -211,7 +211,7 @@ sb_status launch_fg_rhs(sb_sim *s, int what);  // 1: F, G; 3: F, G and RHS fused
 sb_status launch_rhs(sb_sim *s);
 sb_status launch_pressure_bc(sb_sim *s, int guarded);
 sb_status launch_norm_partials(sb_sim *s, int guarded, int *nblocks);
-sb_status launch_adapt_uv(sb_sim *s);
+sb_status launch_adapt_uv(sb_sim *s, int with_prange = 0);
 sb_status launch_pressure_range(sb_sim *s);
 sb_status launch_speed_range(sb_sim *s);
 sb_status launch_cellop(int op, const double *u9, const double *v9, const double *scal,

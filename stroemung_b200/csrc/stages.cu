@@ -490,22 +490,30 @@ __global__ void sum_partials_kernel(const double *__restrict__ partial, int npar
 // u, v for 0 <= x <= NX-2, 0 <= y <= NY-2, every cell (src/simulation.rs:299-311); boundary
 // cells are overwritten afterwards by the restore kernel, fluid cells are final here, so
 // the Fluid-only reductions of calculate_speed_range (src/grid/mod.rs:253-268) fuse in.
+// PRANGE: also the Fluid-only min / max of p (calculate_pressure_range, src/grid/mod.rs:237-251,
+// which the reference runs right before this stage when SOR hit its cap, simulation.rs:283):
+// p is read here anyway.  Partials: 8 doubles per block (smin, smax, umax, vmax, pmin, pmax).
+constexpr int RANGE_RPB = 8;  // rows per block of the velocity-update kernel
+template <bool PRANGE>
 __global__ void adapt_uv_kernel(Geom g, const double *__restrict__ p,
                                 const double *__restrict__ f, const double *__restrict__ gq,
                                 const uint8_t *__restrict__ cflag, double *__restrict__ u,
                                 double *__restrict__ v, double *__restrict__ partial,
                                 double delt, double delx, double dely) {
-    int64_t lx = g.own0 + blockIdx.x;
-    int64_t gx = g.gx0 + lx;
-    double smin = DBL_MAX, smax = 0.0, umax = 0.0, vmax = 0.0;
+    double smin = DBL_MAX, smax = 0.0, umax = 0.0, vmax = 0.0, pmin = DBL_MAX, pmax = 0.0;
     const double dtdx = delt / delx, dtdy = delt / dely;
-    if (lx < g.own1 && gx >= 0 && gx < g.NX) {
+    for (int r = 0; r < RANGE_RPB; r++) {  // RANGE_RPB rows per block: 8x fewer partials
+        const int64_t lx = g.own0 + (int64_t)blockIdx.x * RANGE_RPB + r;
+        const int64_t gx = g.gx0 + lx;
+        if (!(lx < g.own1 && gx >= 0 && gx < g.NX)) continue;
         for (int64_t y = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; y < g.NY;
              y += (int64_t)gridDim.y * blockDim.x) {
             int64_t c = lx * g.pitch + y;
-            double un, vn;
-            if (gx <= g.NX - 2 && y <= g.NY - 2) {
-                double pc = p[c];
+            double un, vn, pc = 0.0;
+            const bool inner = gx <= g.NX - 2 && y <= g.NY - 2;
+            const bool fluid = cf_is_fluid(cflag[c]);
+            if (inner || (PRANGE && fluid)) pc = p[c];
+            if (inner) {
                 un = f[c] - dtdx * (p[c + g.pitch] - pc);
                 vn = gq[c] - dtdy * (p[c + 1] - pc);
                 u[c] = un;
@@ -514,30 +522,40 @@ __global__ void adapt_uv_kernel(Geom g, const double *__restrict__ p,
                 un = u[c];
                 vn = v[c];
             }
-            if (cf_is_fluid(cflag[c])) {
+            if (fluid) {
                 double sq = (un * un) + (vn * vn);
                 smin = fmin(smin, sq);
                 smax = fmax(smax, sq);
                 umax = fmax(umax, fabs(un));
                 vmax = fmax(vmax, fabs(vn));
+                if (PRANGE) {
+                    pmin = fmin(pmin, pc);
+                    pmax = fmax(pmax, pc);
+                }
             }
         }
     }
-    __shared__ double sh[4][TPB / 32];
+    constexpr int NV = PRANGE ? 6 : 4;
+    __shared__ double sh[NV][TPB / 32];
     smin = warp_min(smin); smax = warp_max(smax); umax = warp_max(umax); vmax = warp_max(vmax);
+    if (PRANGE) { pmin = warp_min(pmin); pmax = warp_max(pmax); }
     if ((threadIdx.x & 31) == 0) {
         int w = threadIdx.x >> 5;
         sh[0][w] = smin; sh[1][w] = smax; sh[2][w] = umax; sh[3][w] = vmax;
+        if (PRANGE) { sh[4][w] = pmin; sh[5][w] = pmax; }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int k = 1; k < TPB / 32; k++) {
             smin = fmin(smin, sh[0][k]); smax = fmax(smax, sh[1][k]);
             umax = fmax(umax, sh[2][k]); vmax = fmax(vmax, sh[3][k]);
+            if (PRANGE) { pmin = fmin(pmin, sh[4][k]); pmax = fmax(pmax, sh[5][k]); }
         }
         int64_t blk = (int64_t)blockIdx.x * gridDim.y + blockIdx.y;
-        partial[4 * blk + 0] = smin; partial[4 * blk + 1] = smax;
-        partial[4 * blk + 2] = umax; partial[4 * blk + 3] = vmax;
+        constexpr int ST = PRANGE ? 8 : 4;
+        partial[ST * blk + 0] = smin; partial[ST * blk + 1] = smax;
+        partial[ST * blk + 2] = umax; partial[ST * blk + 3] = vmax;
+        if (PRANGE) { partial[ST * blk + 4] = pmin; partial[ST * blk + 5] = pmax; }
     }
 }
 
@@ -594,27 +612,32 @@ __global__ void range_kernel(Geom g, const double *__restrict__ a, const double 
     }
 }
 
-// final min/max/max/max over block partials -> out[0..3] (f64::MAX, 0.0 fold seeds)
+// final min/max/max/max (and, with stride 8, a second min/max) over block partials -> out
+// (f64::MAX, 0.0 fold seeds)
 __global__ void range_final_kernel(const double *__restrict__ partial, int64_t nblk,
-                                   double *__restrict__ out) {
-    double mn = DBL_MAX, mx = 0.0, m2 = 0.0, m3 = 0.0;
+                                   double *__restrict__ out, int stride) {
+    double mn = DBL_MAX, mx = 0.0, m2 = 0.0, m3 = 0.0, pn = DBL_MAX, px = 0.0;
     for (int64_t i = threadIdx.x; i < nblk; i += blockDim.x) {
-        mn = fmin(mn, partial[4 * i + 0]); mx = fmax(mx, partial[4 * i + 1]);
-        m2 = fmax(m2, partial[4 * i + 2]); m3 = fmax(m3, partial[4 * i + 3]);
+        const double *q = partial + stride * i;
+        mn = fmin(mn, q[0]); mx = fmax(mx, q[1]);
+        m2 = fmax(m2, q[2]); m3 = fmax(m3, q[3]);
+        if (stride == 8) { pn = fmin(pn, q[4]); px = fmax(px, q[5]); }
     }
-    __shared__ double sh[4][1024 / 32];
+    __shared__ double sh[6][1024 / 32];
     mn = warp_min(mn); mx = warp_max(mx); m2 = warp_max(m2); m3 = warp_max(m3);
+    pn = warp_min(pn); px = warp_max(px);
     if ((threadIdx.x & 31) == 0) {
         int w = threadIdx.x >> 5;
-        sh[0][w] = mn; sh[1][w] = mx; sh[2][w] = m2; sh[3][w] = m3;
+        sh[0][w] = mn; sh[1][w] = mx; sh[2][w] = m2; sh[3][w] = m3; sh[4][w] = pn; sh[5][w] = px;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int k = 1; k < (int)(blockDim.x >> 5); k++) {
             mn = fmin(mn, sh[0][k]); mx = fmax(mx, sh[1][k]);
             m2 = fmax(m2, sh[2][k]); m3 = fmax(m3, sh[3][k]);
+            pn = fmin(pn, sh[4][k]); px = fmax(px, sh[5][k]);
         }
-        out[0] = mn; out[1] = mx; out[2] = m2; out[3] = m3;
+        out[0] = mn; out[1] = mx; out[2] = m2; out[3] = m3; out[4] = pn; out[5] = px;
     }
 }
 
@@ -778,28 +801,37 @@ sb_status reduce_norm(sb_sim *s, int nparts, double *out) {
     return SB_OK;
 }
 
-static sb_status finish_ranges(sb_sim *s, int64_t nblk, double out[4]) {
-    range_final_kernel<<<1, 1024, 0, s->stream>>>(s->d_partial, nblk, s->d_scalars);
+// stride 4: out[0..3]; stride 8: out[0..5] (the fused pressure range in out[4..5])
+static sb_status finish_ranges(sb_sim *s, int64_t nblk, double *out, int stride = 4) {
+    range_final_kernel<<<1, 1024, 0, s->stream>>>(s->d_partial, nblk, s->d_scalars, stride);
     s->launches++;
-    sb_status st = slab_allreduce(s, s->d_scalars, 4,
-                                  XR_MIN | (XR_MAX << 2) | (XR_MAX << 4) | (XR_MAX << 6));
+    const int n = stride == 8 ? 6 : 4;
+    sb_status st = slab_allreduce(s, s->d_scalars, n,
+                                  XR_MIN | (XR_MAX << 2) | (XR_MAX << 4) | (XR_MAX << 6) |
+                                      (XR_MIN << 8) | (XR_MAX << 10));
     if (st) return st;
-    SB_CUDA(cudaMemcpyAsync(s->h_scalars, s->d_scalars, 4 * sizeof(double),
+    SB_CUDA(cudaMemcpyAsync(s->h_scalars, s->d_scalars, n * sizeof(double),
                             cudaMemcpyDeviceToHost, s->stream));
     SB_CUDA(cudaStreamSynchronize(s->stream));
-    for (int i = 0; i < 4; i++) out[i] = s->h_scalars[i];
+    for (int i = 0; i < n; i++) out[i] = s->h_scalars[i];
     return SB_OK;
 }
 
-sb_status launch_adapt_uv(sb_sim *s) {
-    int64_t rows = s->g.own1 - s->g.own0;
+// with_prange: also grid.calculate_pressure_range() (the caller skipped it after a capped solve)
+sb_status launch_adapt_uv(sb_sim *s, int with_prange) {
+    const int64_t rows = (s->g.own1 - s->g.own0 + RANGE_RPB - 1) / RANGE_RPB;  // block rows
     unsigned gx = (unsigned)((s->g.NY + 4 * TPB - 1) / (4 * TPB));
     if (gx < 1) gx = 1;
-    sb_status st = ensure_partial(s, (size_t)gx * rows * 4 + 64);
+    sb_status st = ensure_partial(s, (size_t)gx * rows * 8 + 64);
     if (st) return st;
-    adapt_uv_kernel<<<dim3((unsigned)rows, gx), TPB, 0, s->stream>>>(
-        s->g, s->p[s->cur], s->f, s->gq, s->cflag, s->u, s->v, s->d_partial, s->prm.delt,
-        s->prm.delx, s->prm.dely);
+    if (with_prange)
+        adapt_uv_kernel<true><<<dim3((unsigned)rows, gx), TPB, 0, s->stream>>>(
+            s->g, s->p[s->cur], s->f, s->gq, s->cflag, s->u, s->v, s->d_partial, s->prm.delt,
+            s->prm.delx, s->prm.dely);
+    else
+        adapt_uv_kernel<false><<<dim3((unsigned)rows, gx), TPB, 0, s->stream>>>(
+            s->g, s->p[s->cur], s->f, s->gq, s->cflag, s->u, s->v, s->d_partial, s->prm.delt,
+            s->prm.delx, s->prm.dely);
     s->launches++;
     if (s->bl.n) {
         int nb = (int)((s->bl.n + TPB - 1) / TPB);
@@ -815,14 +847,18 @@ sb_status launch_adapt_uv(sb_sim *s) {
         if ((st = slab_put_rows(s, s->u, s->lo_u, s->hi_u, 8))) return st;
         if ((st = slab_put_rows(s, s->v, s->lo_v, s->hi_v, 8))) return st;
     }
-    double out[4];
-    st = finish_ranges(s, (int64_t)gx * rows, out);
+    double out[6];
+    st = finish_ranges(s, (int64_t)gx * rows, out, with_prange ? 8 : 4);
     if (st) return st;
     // sqrt of the folded min / max (src/grid/mod.rs:267)
     s->speed_range[0] = sqrt(out[0]);
     s->speed_range[1] = sqrt(out[1]);
     s->umax = out[2];
     s->vmax = out[3];
+    if (with_prange) {
+        s->pressure_range[0] = out[4];
+        s->pressure_range[1] = out[5];
+    }
     return SB_OK;
 }
 
@@ -893,7 +929,8 @@ void preload_stages() {
     cudaFuncGetAttributes(&a, norm_partial_kernel);
     cudaFuncGetAttributes(&a, sor_finalize_kernel);
     cudaFuncGetAttributes(&a, sum_partials_kernel);
-    cudaFuncGetAttributes(&a, adapt_uv_kernel);
+    cudaFuncGetAttributes(&a, adapt_uv_kernel<false>);
+    cudaFuncGetAttributes(&a, adapt_uv_kernel<true>);
     cudaFuncGetAttributes(&a, restore_uv_kernel);
     cudaFuncGetAttributes(&a, range_kernel);
     cudaFuncGetAttributes(&a, range_final_kernel);

@@ -497,3 +497,79 @@ def test_render_degenerate_range():
     for ct in ("pressure", "speed"):
         assert np.array_equal(sim.render_simulation(ct), o.render_simulation(ct))
     sim.close()
+
+
+# ---- streaming kernel with boundary cells inside its items: straight walls along x and the
+#      boundary rows at the ends of the grid (sor_rb_stream.cu, section 3a of DESIGN.md) ------
+def _ring(nx, ny, kinds):
+    """kind array with the given ring kinds (y-walls, x=0 row, x=nx-1 row); velocities 0 / inflow 1"""
+    kind = np.zeros((nx, ny), dtype=np.uint8)
+    bu = np.zeros((nx, ny))
+    bv = np.zeros((nx, ny))
+    wall, lo, hi = kinds
+    kind[0, :] = lo
+    kind[nx - 1, :] = hi
+    kind[:, 0] = wall
+    kind[:, ny - 1] = wall
+    bu[kind == 3] = 1.0
+    return kind, bu, bv
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 4])
+@pytest.mark.parametrize("shape,kinds,obstacle", [
+    ((200, 300), (1, 1, 1), None),            # closed box: walls at both ends in x too
+    ((260, 300), (1, 3, 2), None),            # channel
+    ((260, 301), (1, 3, 2), None),            # odd NY: the last strip cannot start 16-byte aligned
+    ((300, 120), (1, 3, 2), None),            # narrower than one strip
+    ((240, 420), (1, 3, 2), (0, 40, 60, 90)),  # a block on the inflow row: not a plain end row
+    ((240, 420), (1, 3, 2), (100, 0, 130, 50)),  # a block on the wall: the wall strip is cut
+])
+def test_red_black_walls_and_end_rows_in_stream(shape, kinds, obstacle, T):
+    nx, ny = shape
+    kind, bu, bv = _ring(nx, ny, kinds)
+    if obstacle:
+        x0, y0, x1, y1 = obstacle
+        kind[x0:x1, y0:y1] = 1
+        bu[x0:x1, y0:y1] = 0.0
+    p, u, v = random_fields(nx, ny, 77 + T)
+    unf = unfinalized(nx, ny, kind, bu, bv, p=p, u=u, v=v)
+    sim = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK, temporal_block=T)
+    o = oracle_from(unf, sor_mode=po.SOR_RED_BLACK)
+    n = 2 * T + 3   # full passes and a shortened last one
+    norms = sim.sor_sweeps(n)
+    for k in range(n):
+        o.sor_sweep()
+        assert close(norms[k], o.calculate_norm_squared()), (k, norms[k])
+    assert_bits_equal(sim.grid.pressure, o.p, "p after red-black sweeps")
+    for t in range(2):
+        it, nrm = sim.run_simulation_tick()
+        oit, onrm = o.run_simulation_tick()
+        assert it == oit and close(nrm, onrm), (t, it, oit, nrm, onrm)
+    assert_bits_equal(sim.grid.pressure, o.p, "p after ticks")
+    assert_bits_equal(sim.grid.u, o.u, "u after ticks")
+    assert sim.grid.pressure_range == list(o.state().pressure_range)
+    assert sim.grid.speed_range == list(o.state().speed_range)
+    sim.close()
+
+
+def test_stream_kinds_env_gives_identical_fields(monkeypatch):
+    """whatever subset of item kinds the streaming kernel takes, the fields are the same bits"""
+    nx, ny = 300, 380
+    kind, bu, bv = _ring(nx, ny, (1, 3, 2))
+    p, u, v = random_fields(nx, ny, 5)
+    unf = unfinalized(nx, ny, kind, bu, bv, p=p, u=u, v=v)
+    ref = None
+    for kinds in ("0", "1", "2", "3"):
+        monkeypatch.setenv("SB_RB_STREAM_KINDS", kinds)
+        sim = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK, temporal_block=4)
+        for _ in range(2):
+            sim.run_simulation_tick()
+        got = (sim.grid.pressure, sim.grid.u, sim.grid.v, sim.rb_plan)
+        sim.close()
+        if ref is None:
+            ref = got
+            assert got[3][1] > 0          # some streaming items even with plain strips only
+        else:
+            for a, b, name in zip(ref[:3], got[:3], "puv"):
+                assert_bits_equal(a, b, f"{name} with kinds {kinds}")
+    assert got[3][0] < ref[3][0]          # all kinds: fewer tiles left for the tile kernel
