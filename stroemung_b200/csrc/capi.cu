@@ -12,7 +12,7 @@
 #include <algorithm>
 #include <new>
 
-#include "sb_internal.cuh"
+#include "sor_rb.cuh"
 
 namespace sb {
 
@@ -309,15 +309,23 @@ static sb_status solve(sb_sim *s, uint32_t max_it, int test_exit, uint32_t *iter
     while (true) {
         uint32_t batch = std::min<uint32_t>(std::max<uint32_t>(hint, 1), 256);
         for (uint32_t b = 0; b < batch; b++) {
-            int nparts = 0;
+            int nparts = 0, fused = 0;
             if (rb) {
-                if ((st = launch_sor_rb_pass(s, &nparts, 0))) return st;
+                RbFin fin{};
+                fin.enabled = 1;
+                fin.test_exit = test_exit;
+                fin.fluid_cells = s->fluid_cells;
+                fin.initial_norm = init;
+                fin.eps2 = eps2;
+                fin.norm_hist = d_hist;
+                if ((st = launch_sor_rb_pass(s, &nparts, 0, &fin, &fused))) return st;
             } else {
                 if ((st = launch_pressure_bc(s, 1))) return st;
                 if ((st = launch_sor_lex_sweep(s, 1))) return st;
                 if ((st = launch_norm_partials(s, 1, &nparts))) return st;
             }
-            if ((st = launch_sor_finalize(s, nparts, init, eps2, test_exit, d_hist))) return st;
+            if (!fused)
+                if ((st = launch_sor_finalize(s, nparts, init, eps2, test_exit, d_hist))) return st;
             enq++;
         }
         SB_CUDA(cudaMemcpyAsync(h, s->d_ctl, sizeof(SorCtl), cudaMemcpyDeviceToHost, s->stream));

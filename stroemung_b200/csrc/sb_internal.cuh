@@ -111,6 +111,7 @@ struct RbPlan {
     int32_t *d_slow = nullptr;   // tile ids of the slow tiles
     RbItem *d_items = nullptr;
     uint8_t *d_plain = nullptr;  // scratch: one byte per tile
+    unsigned *d_counter = nullptr;  // CTAs of the streaming kernel done (fused finalize)
     size_t cap_tiles = 0, cap_items = 0;
 };
 
@@ -219,11 +220,15 @@ sb_status launch_cellop(int op, const double *u9, const double *v9, const double
 // sor_lex.cu
 sb_status launch_sor_lex_sweep(sb_sim *s, int guarded);
 // sor_rb.cu
-sb_status launch_sor_rb_pass(sb_sim *s, int *ntiles, int norm_only);
+struct RbFin;
+// fin != nullptr and *fused set: the pass also did the work of launch_sor_finalize
+sb_status launch_sor_rb_pass(sb_sim *s, int *ntiles, int norm_only, const RbFin *fin = nullptr,
+                             int *fused = nullptr);
 int rb_halo_rows(int T);
 // sor_rb_stream.cu
 sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h);
-sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h);
+sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h,
+                               const RbFin *fin);
 void rb_plan_release(sb_sim *s);
 void preload_sor_rb_stream();
 // profiling hooks (capi.cu): record an event of the current pass on the stream

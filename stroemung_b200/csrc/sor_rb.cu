@@ -638,7 +638,8 @@ static bool rb_stream_enabled() {
 // one guarded pass: performs ctl->active_T sweeps from pbuf[ctl->src] into the other buffer
 // (norm_only: just the residual partial sums of pbuf[ctl->src]).  The all-fluid part of the
 // grid goes to the streaming kernel (sor_rb_stream.cu), everything else to the tile kernel.
-sb_status launch_sor_rb_pass(sb_sim *s, int *nparts_out, int norm_only) {
+sb_status launch_sor_rb_pass(sb_sim *s, int *nparts_out, int norm_only, const RbFin *fin,
+                             int *fused) {
     sb_status st = ensure_tmaps(s);
     if (st) return st;
     const Geom &g = s->g;
@@ -683,8 +684,13 @@ sb_status launch_sor_rb_pass(sb_sim *s, int *nparts_out, int norm_only) {
                                                       tile_list);
         s->launches++;
     }
+    if (fused) *fused = 0;
     if (n_items > 0) {
-        if ((st = launch_sor_rb_stream(s, n_tile, nparts, h))) return st;
+        // single GPU: the streaming kernel's last CTA finalizes the pass (a slab run needs
+        // the all-gather of sor_finalize_kernel)
+        const RbFin *f = (fin && fused && !s->slab) ? fin : nullptr;
+        if ((st = launch_sor_rb_stream(s, n_tile, nparts, h, f))) return st;
+        if (f) *fused = 1;
     }
     if (!norm_only) prof_mark(s);
     SB_CUDA(cudaGetLastError());

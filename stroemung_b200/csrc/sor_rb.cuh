@@ -80,6 +80,50 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
         : "memory");
 }
 
+// finalize of a pass done by the streaming kernel's last CTA (single GPU): what the separate
+// sor_finalize_kernel (stages.cu) would be launched with
+struct RbFin {
+    int enabled, test_exit;
+    double fluid_cells, initial_norm, eps2;
+    double *norm_hist;
+    unsigned *counter;   // CTAs done so far (resets itself)
+};
+
+// Exit rule of /root/reference/src/simulation.rs:279 on the T norms of a pass and the
+// bookkeeping that follows (one thread).  A red-black pass runs T sweeps speculatively; if
+// the rule fires at level k < T the pass is repeated from the same source buffer with T = k.
+__device__ __forceinline__ void sor_advance_ctl(SorCtl *ctl, const double *level_norm, int T,
+                                                double initial_norm, double eps2, int test_exit,
+                                                double *norm_hist) {
+    int exit_at = 0;
+    for (int lvl = 0; lvl < T; lvl++) {
+        ctl->norms[lvl] = level_norm[lvl];
+        if (norm_hist) norm_hist[ctl->iters_done + lvl] = level_norm[lvl];
+        if (test_exit && !exit_at &&
+            ((level_norm[lvl] < initial_norm) || (level_norm[lvl] < eps2)))
+            exit_at = lvl + 1;
+    }
+    if (exit_at && exit_at < T) {
+        ctl->active_T = exit_at;  // redo this pass with fewer sweeps (same source buffer)
+        return;
+    }
+    ctl->iters_done += T;
+    ctl->src ^= (ctl->block_T > 0) ? 1 : 0;  // red-black passes ping-pong; in-place modes don't
+    ctl->last_norm = level_norm[T - 1];
+    if (exit_at) {
+        ctl->active_T = 0;
+        ctl->finished = 1;
+    } else if (ctl->iters_done >= ctl->max_iterations) {
+        ctl->active_T = 0;
+        ctl->finished = 1;
+        ctl->cap_hit = 1;
+    } else {
+        uint32_t rem = ctl->max_iterations - ctl->iters_done;
+        int next = ctl->block_T > 0 ? ctl->block_T : 1;
+        ctl->active_T = (int)(rem < (uint32_t)next ? rem : (uint32_t)next);
+    }
+}
+
 __device__ __forceinline__ double warp_sum_down(double v) {
     for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     return v;

@@ -448,9 +448,8 @@ __device__ __forceinline__ void stream_item_any(SCtx &c, int flags, int gpar, do
 template <int TB>
 __global__ void __launch_bounds__(32 * stream_warps(TB), 1)
 sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict__ pbuf,
-                     const double *__restrict__ rhs, const SorCtl *__restrict__ ctl,
-                     double *__restrict__ partial, int part_base, int part_stride, int64_t pitch,
-                     int gpar, RbConsts k) {
+                     const double *__restrict__ rhs, SorCtl *ctl, double *partial, int part_base,
+                     int part_stride, int64_t pitch, int gpar, RbConsts k, RbFin fin) {
     const int T = ctl->active_T;
     if (T == 0) return;
     const int src = ctl->src;
@@ -467,8 +466,7 @@ sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict
     if (it.x1 <= it.x0) {  // padding: contributes nothing
         if (c.lane == 0)
             for (int i = 0; i < T; i++) part[(int64_t)i * part_stride] = 0.0;
-        return;
-    }
+    } else {
     c.lane_m1 = (c.lane + 31) & 31;
     c.lane_p1 = (c.lane + 1) & 31;
     // rings of the T actually run: p ring, rhs ring, one mbarrier per rhs slot
@@ -503,10 +501,42 @@ sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict
     else if (TB > 2 && T == 2) stream_item_any<2>(c, flags, gpar, part, part_stride);
     else if (TB > 3 && T == 3) stream_item_any<3>(c, flags, gpar, part, part_stride);
     if (trace && c.lane == 0) g_trace[4 * idx + 1] = gtime();
+    }
+    // ---- the last CTA to finish totals the partials of the whole pass (tile kernel's
+    //      included: it ran before), applies the exit rule and advances the control block --
+    //      what sor_finalize_kernel does as a separate launch (single GPU only) ---------------
+    if (!fin.enabled) return;
+    __shared__ int s_last;
+    __shared__ double s_sum[stream_warps(TB)];
+    __shared__ double s_norm[RB_TMAX];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(fin.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int lvl = 0; lvl < T; lvl++) {
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < part_stride; i += blockDim.x)
+            acc += __ldcg(partial + (int64_t)lvl * part_stride + i);
+        acc = warp_sum_down(acc);
+        if (c.lane == 0) s_sum[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < stream_warps(TB); w++) t += s_sum[w];
+            s_norm[lvl] = t / fin.fluid_cells;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        sor_advance_ctl(ctl, s_norm, T, fin.initial_norm, fin.eps2, fin.test_exit, fin.norm_hist);
+        *fin.counter = 0u;
+    }
 }
 
-using StreamKernel = void (*)(const RbItem *, double *const *, const double *, const SorCtl *,
-                              double *, int, int, int64_t, int, RbConsts);
+using StreamKernel = void (*)(const RbItem *, double *const *, const double *, SorCtl *,
+                              double *, int, int, int64_t, int, RbConsts, RbFin);
 StreamKernel stream_kernel(int TB) {
     switch (TB) {
     case 1: return sor_rb_stream_kernel<1>;
@@ -609,6 +639,7 @@ void rb_plan_release(sb_sim *s) {
     cudaFree(s->plan.d_slow);
     cudaFree(s->plan.d_items);
     cudaFree(s->plan.d_plain);
+    cudaFree(s->plan.d_counter);
     s->plan = RbPlan();
 }
 
@@ -795,11 +826,21 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
     return SB_OK;
 }
 
-sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h) {
+sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h,
+                               const RbFin *fin_in) {
     const Geom &g = s->g;
     const int gpar = (int)(((g.gx0 % 2) + 2) % 2);
     const int TB = s->prm.temporal_block;
     const int nw = stream_cta_warps(TB);
+    RbFin fin{};
+    if (fin_in) {
+        fin = *fin_in;
+        if (!s->plan.d_counter) {
+            SB_CUDA(cudaMallocAsync(&s->plan.d_counter, sizeof(unsigned), s->stream));
+            SB_CUDA(cudaMemsetAsync(s->plan.d_counter, 0, sizeof(unsigned), s->stream));
+        }
+        fin.counter = s->plan.d_counter;
+    }
     static int trace_set = 0;
     if (!trace_set && getenv("SB_STREAM_TRACE")) {
         const int one = 1;
@@ -808,7 +849,7 @@ sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h)
     }
     stream_kernel(TB)<<<s->plan.n_items / nw, 32 * nw, stream_smem_bytes(TB), s->stream>>>(
         s->plan.d_items, rb_pbuf_ptr(s), s->rhs, s->d_ctl, s->d_partial, part_base, part_stride,
-        g.pitch, gpar, rb_consts(s));
+        g.pitch, gpar, rb_consts(s), fin);
     s->launches++;
     SB_CUDA(cudaGetLastError());
     return SB_OK;

@@ -10,7 +10,7 @@
 // (paths relative to /root/reference).  Compiled with -fmad=false so that no a*b+c
 // is contracted; see cellops.cuh for the operator restatements.
 #include "cellops.cuh"
-#include "sb_internal.cuh"
+#include "sor_rb.cuh"
 #include "slab_dev.cuh"
 
 #include <float.h>
@@ -441,33 +441,7 @@ __global__ void sor_finalize_kernel(SorCtl *__restrict__ ctl, const double *__re
     if ((int)threadIdx.x < T) level_norm[threadIdx.x] = level_sum[threadIdx.x] / fluid_cells;
     __syncthreads();
     if (threadIdx.x != 0) return;
-    int exit_at = 0;
-    for (int lvl = 0; lvl < T; lvl++) {
-        ctl->norms[lvl] = level_norm[lvl];
-        if (norm_hist) norm_hist[ctl->iters_done + lvl] = level_norm[lvl];
-        if (test_exit && !exit_at &&
-            ((level_norm[lvl] < initial_norm) || (level_norm[lvl] < eps2)))
-            exit_at = lvl + 1;
-    }
-    if (exit_at && exit_at < T) {
-        ctl->active_T = exit_at;  // redo this pass with fewer sweeps (same source buffer)
-        return;
-    }
-    ctl->iters_done += T;
-    ctl->src ^= (ctl->block_T > 0) ? 1 : 0;  // red-black passes ping-pong; in-place modes don't
-    ctl->last_norm = level_norm[T - 1];
-    if (exit_at) {
-        ctl->active_T = 0;
-        ctl->finished = 1;
-    } else if (ctl->iters_done >= ctl->max_iterations) {
-        ctl->active_T = 0;
-        ctl->finished = 1;
-        ctl->cap_hit = 1;
-    } else {
-        uint32_t rem = ctl->max_iterations - ctl->iters_done;
-        int next = ctl->block_T > 0 ? ctl->block_T : 1;
-        ctl->active_T = (int)(rem < (uint32_t)next ? rem : (uint32_t)next);
-    }
+    sor_advance_ctl(ctl, level_norm, T, initial_norm, eps2, test_exit, norm_hist);
 }
 
 // out[0] = (sum of partial[0..n)) / fluid_cells, same tree as the finalize kernel
