@@ -306,7 +306,13 @@ static sb_status solve(sb_sim *s, uint32_t max_it, int test_exit, uint32_t *iter
     uint32_t total_passes = (max_it + T - 1) / T + 1;  // +1: a possible shortened redo pass
     uint32_t hint = s->sor_batch_hint ? s->sor_batch_hint : 4;
     uint32_t enq = 0;
-    while (true) {
+    const bool small = rb && max_it > 0 && sor_small_fits(s);
+    if (small) {  // the whole solve in one launch (sor_small.cu)
+        if ((st = launch_sor_small(s, init, eps2, test_exit, d_hist))) return st;
+        SB_CUDA(cudaMemcpyAsync(h, s->d_ctl, sizeof(SorCtl), cudaMemcpyDeviceToHost, s->stream));
+        SB_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    while (!small) {
         uint32_t batch = std::min<uint32_t>(std::max<uint32_t>(hint, 1), 256);
         for (uint32_t b = 0; b < batch; b++) {
             int nparts = 0, fused = 0;

@@ -231,6 +231,11 @@ sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h,
                                const RbFin *fin);
 void rb_plan_release(sb_sim *s);
 void preload_sor_rb_stream();
+// sor_small.cu: the whole red-black solve of a grid that fits one SM's shared memory
+bool sor_small_fits(const sb_sim *s);
+sb_status launch_sor_small(sb_sim *s, double initial_norm, double eps2, int test_exit,
+                           double *norm_hist);
+void preload_sor_small();
 // profiling hooks (capi.cu): record an event of the current pass on the stream
 void prof_mark(sb_sim *s);
 // finalize (stages.cu): sum partials, exit test, update ctl

@@ -178,6 +178,7 @@ sb_status slab_prepare(sb_sim *s) {
     preload_sor_rb();
     preload_sor_rb_stream();
     preload_render();
+    preload_sor_small();
     s->slab = true;
     s->connected = false;
     memset(&s->link, 0, sizeof(s->link));

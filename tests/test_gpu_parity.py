@@ -20,6 +20,16 @@ from tests.util import (DEFAULTS, assert_bits_equal, oracle_from, random_fields,
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["small-grid-kernel", "pass-kernels"])
+def sor_small_switch(request, monkeypatch):
+    """Grids of up to 12 288 cells take the one-launch solve (sor_small.cu) by default; every
+    test here also runs with that path switched off, so the small shapes keep exercising the
+    tile / streaming pass kernels."""
+    if request.param == "pass-kernels":
+        monkeypatch.setenv("SB_SOR_SMALL", "0")
+    yield
+
 TICK = "stroemung__simulation__tests__simulation_tick"
 NORM_RTOL = 1e-12
 
