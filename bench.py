@@ -298,6 +298,7 @@ def run_ours(args):
     clocks = sampler.stop()
     pass_ms = sim.profile_read()
     rb_plan = list(sim.rb_plan) if args.mode == "rb" else None
+    sor_path, sor_ctas = sim.sor_path if args.mode == "rb" else (0, 0)
     sim.profile_enable(False)
     launches = sim.kernel_launches - launches0
     dt, sor_ms = max_over_ranks(dt), max_over_ranks(sor_ms)
@@ -348,9 +349,12 @@ def run_ours(args):
         key = f"{args.mode}-T{T}-{rows}x{ny}"
         traffic = ncu_traffic(key)
         roof = {"bound": "hbm",
-                "kernel": (f"SOR pass = sor_rb_stream_kernel<{T}> on {rb_plan[1]} work items + "
-                           f"sor_rb_kernel on {rb_plan[0]} tiles") if args.mode == "rb"
-                else "sor_lex_kernel",
+                "kernel": "sor_lex_kernel" if args.mode != "rb" else
+                (f"SOR pass = sor_rb_stream_kernel<{T}> on {rb_plan[1]} work items + "
+                 f"sor_rb_kernel on {rb_plan[0]} tiles") if sor_path == 0 else
+                "whole solve = sor_small_kernel (one SM)" if sor_path == 1 else
+                f"whole solve = {'sor_mid_reg_kernel' if sor_path == 3 else 'sor_mid_kernel'}, "
+                f"grid resident in the shared memory of {sor_ctas} SMs (cooperative launch)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "dram_gbs": traffic / (avg_ms * 1e-3) / 1e9 if traffic else None,
@@ -377,6 +381,7 @@ def run_ours(args):
                          f"{r['ticks']} ticks, {r['sweeps']} lexicographic sweeps, "
                          f"{r['seconds']:.1f} s, C oracle (port of the Rust reference), 1 thread"}
 
+    ws_mb = local_cells * 57 / 1e6   # 7 f64 arrays + flags
     kfix = TICK_FIXED_BYTES_PER_CELL
     k_avg = total_sweeps / max(args.steps, 1)
     line = {
@@ -387,8 +392,14 @@ def run_ours(args):
                    "temporal_block": T, "sweeps_per_tick": k_avg,
                    "slabs": f"{n_gpus} row slab(s) along x",
                    "rb_plan": {"tile_kernel_tiles": rb_plan[0], "stream_items": rb_plan[1]}
-                   if rb_plan else None,
-                   "l2": "working set 3.8 GB per GPU >> 126 MB L2, no flush needed"},
+                   if rb_plan and sor_path == 0 else None,
+                   "sor_path": ["pass kernels", "sor_small (one launch, one SM)",
+                                f"sor_mid (one launch, {sor_ctas} SMs)",
+                                f"sor_mid_reg (one launch, {sor_ctas} SMs)"][sor_path],
+                   "l2": (f"working set {ws_mb / 1e3:.1f} GB per GPU >> 126 MB L2, no flush needed"
+                          if ws_mb > 1000 else
+                          f"working set {ws_mb:.0f} MB per GPU: not flushed between ticks (a "
+                          f"tick rewrites every array; secondary workload, not the headline)")},
         "sor": {"gcell_sweeps_per_s": cells * total_sweeps / (sor_ms * 1e-3) / 1e9
                 if sor_ms else None,
                 "algorithmic_gbs": SOR_BYTES_PER_CELL_SWEEP * cells * total_sweeps /

@@ -251,6 +251,11 @@ double sb_last_sor_ms(const sb_sim *sim);
 /* how the last red-black pass split the grid: tiles on the tile kernel (walls, obstacles,
  * grid ring, slab edges) and work items of the streaming kernel (all-fluid regions) */
 sb_status sb_rb_plan(const sb_sim *sim, int32_t *tile_kernel_tiles, int32_t *stream_items);
+/* which kernels ran the last red-black solve_sor (simulation.rs:239-285): 0 pass by pass (tile +
+ * streaming kernels), 1 one launch on one SM (small grids), 2 / 3 one cooperative launch with
+ * the grid resident in the shared memory (2) or the registers + shared memory (3) of `*ctas`
+ * SMs (mid-size grids); ctas may be NULL */
+int32_t sb_last_sor_path(const sb_sim *sim, int32_t *ctas);
 /* per-pass profiling of the dominant kernel: when enabled, every SOR sweep-kernel launch
  * (red-black pass or wavefront sweep) is bracketed by CUDA events on the handle's stream.
  * sb_profile_read returns the durations (ms) recorded since the last read, oldest first;

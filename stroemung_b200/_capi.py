@@ -71,7 +71,7 @@ SYMBOLS = [
     "sb_slab_export", "sb_slab_connect", "sb_slab_sync_halos", "sb_du2dx", "sb_duvdx", "sb_duvdy",
     "sb_dv2dy", "sb_laplacian", "sb_residual", "sb_calculate_f", "sb_calculate_g",
     "sb_profile_enable", "sb_profile_read", "sb_timer_begin", "sb_timer_end", "sb_kernel_launches", "sb_last_sor_ms", "sb_stream",
-    "sb_rb_plan",
+    "sb_rb_plan", "sb_last_sor_path",
     "sb_version",
 ]
 
@@ -132,6 +132,7 @@ def lib():
         "sb_timer_end": ([vp, dp], C.c_int),
         "sb_kernel_launches": ([vp], C.c_uint64),
         "sb_rb_plan": ([vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)], C.c_int),
+        "sb_last_sor_path": ([vp, C.POINTER(C.c_int32)], C.c_int32),
         "sb_last_sor_ms": ([vp], C.c_double),
         "sb_stream": ([vp], vp),
         "sb_version": ([], C.c_char_p),

@@ -62,6 +62,7 @@ static void destroy(sb_sim *s) {
     slab_release(s);
     rb_plan_release(s);
     cudaFree(s->d_hist);
+    cudaFree(s->d_mid);
     cudaFree(s->d_img);
     cudaFree(s->p[0]); cudaFree(s->p[1]); cudaFree(s->u); cudaFree(s->v); cudaFree(s->f);
     cudaFree(s->gq); cudaFree(s->rhs); cudaFree(s->cflag);
@@ -307,12 +308,29 @@ static sb_status solve(sb_sim *s, uint32_t max_it, int test_exit, uint32_t *iter
     uint32_t hint = s->sor_batch_hint ? s->sor_batch_hint : 4;
     uint32_t enq = 0;
     const bool small = rb && max_it > 0 && sor_small_fits(s);
-    if (small) {  // the whole solve in one launch (sor_small.cu)
-        if ((st = launch_sor_small(s, init, eps2, test_exit, d_hist))) return st;
+    const bool mid = rb && max_it > 0 && !small && sor_mid_fits(s);
+    if (small || mid) {  // the whole solve in one launch (sor_small.cu / sor_mid.cu)
+        s->last_sor_path = small ? 1 : 2;
+        s->last_sor_ctas = 1;
+        if (small) st = launch_sor_small(s, init, eps2, test_exit, d_hist);
+        else st = launch_sor_mid(s, init, eps2, test_exit, d_hist);
+        if (st) return st;
         SB_CUDA(cudaMemcpyAsync(h, s->d_ctl, sizeof(SorCtl), cudaMemcpyDeviceToHost, s->stream));
         SB_CUDA(cudaStreamSynchronize(s->stream));
+        if (h->pad) {
+            set_error("SOR grid barrier timed out (sor_mid.cu)");
+            return SB_CUDA_ERROR;
+        }
+        if (mid && s->last_sor_path == 3 && getenv("SB_MID_TRACE")) {
+            const double n = std::max(1u, h->iters_done);
+            fprintf(stderr, "sor_mid_reg: %u sweeps; cycles per sweep on CTA 0: BC %.0f, red %.0f, "
+                            "black %.0f, red residual + publish %.0f, grid barrier %.0f, halo + "
+                            "norm %.0f\n", h->iters_done, h->norms[1] / n, h->norms[2] / n,
+                    h->norms[3] / n, h->norms[4] / n, h->norms[5] / n, h->norms[6] / n);
+        }
     }
-    while (!small) {
+    if (!small && !mid) s->last_sor_path = 0;
+    while (!small && !mid) {
         uint32_t batch = std::min<uint32_t>(std::max<uint32_t>(hint, 1), 256);
         for (uint32_t b = 0; b < batch; b++) {
             int nparts = 0, fused = 0;
@@ -894,6 +912,12 @@ sb_status sb_rb_plan(const sb_sim *sim, int32_t *tile_kernel_tiles, int32_t *str
     return SB_OK;
 }
 uint64_t sb_kernel_launches(const sb_sim *sim) { return sim ? sim->launches : 0; }
+
+int32_t sb_last_sor_path(const sb_sim *sim, int32_t *ctas) {
+    if (!sim) return 0;
+    if (ctas) *ctas = sim->last_sor_path ? sim->last_sor_ctas : 0;
+    return sim->last_sor_path;
+}
 double sb_last_sor_ms(const sb_sim *sim) { return sim ? sim->last_sor_ms : 0.0; }
 void *sb_stream(const sb_sim *sim) { return sim ? (void *)sim->stream : nullptr; }
 const char *sb_version(void) { return "stroemung_b200 0.1.0 (sm_100a)"; }

@@ -193,6 +193,9 @@ struct sb_sim {
     double *lo_rhs = nullptr, *hi_rhs = nullptr;
     double *d_hist = nullptr;                 // norm history of sb_sor_sweeps (grows only)
     size_t hist_cap = 0;
+    void *d_mid = nullptr;                    // sor_mid.cu: barrier word, exchange rows, partials
+    size_t mid_cap = 0;
+    int last_sor_path = 0, last_sor_ctas = 0;  // sb_last_sor_path
     uchar4 *d_img = nullptr;                  // RGBA8 frame of sb_render_rgba (lazy)
     // tensor maps for the red-black pass (built lazily per buffer)
     bool tmaps_ready = false;
@@ -236,6 +239,11 @@ bool sor_small_fits(const sb_sim *s);
 sb_status launch_sor_small(sb_sim *s, double initial_norm, double eps2, int test_exit,
                            double *norm_hist);
 void preload_sor_small();
+// sor_mid.cu: the whole red-black solve of a grid that fits the shared memory of all SMs
+bool sor_mid_fits(const sb_sim *s);
+sb_status launch_sor_mid(sb_sim *s, double initial_norm, double eps2, int test_exit,
+                         double *norm_hist);
+void preload_sor_mid();
 // profiling hooks (capi.cu): record an event of the current pass on the stream
 void prof_mark(sb_sim *s);
 // finalize (stages.cu): sum partials, exit test, update ctl

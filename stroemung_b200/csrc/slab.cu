@@ -179,6 +179,7 @@ sb_status slab_prepare(sb_sim *s) {
     preload_sor_rb_stream();
     preload_render();
     preload_sor_small();
+    preload_sor_mid();
     s->slab = true;
     s->connected = false;
     memset(&s->link, 0, sizeof(s->link));

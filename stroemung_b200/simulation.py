@@ -351,6 +351,15 @@ class Simulation:
         self._check(_capi.lib().sb_rb_plan(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    @property
+    def sor_path(self):
+        """(path, ctas) of the last red-black solve: 0 pass by pass, 1 one launch on one SM
+        (sor_small.cu), 2 / 3 one cooperative launch over `ctas` SMs (sor_mid.cu: generic /
+        register-window kernel)"""
+        n = C.c_int32()
+        path = _capi.lib().sb_last_sor_path(self._h, C.byref(n))
+        return int(path), int(n.value)
+
     def timer_begin(self):
         self._check(_capi.lib().sb_timer_begin(self._h))
 

@@ -21,14 +21,24 @@ from tests.util import (DEFAULTS, assert_bits_equal, oracle_from, random_fields,
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["small-grid-kernel", "pass-kernels"])
-def sor_small_switch(request, monkeypatch):
-    """Grids of up to 12 288 cells take the one-launch solve (sor_small.cu) by default; every
-    test here also runs with that path switched off, so the small shapes keep exercising the
-    tile / streaming pass kernels."""
-    if request.param == "pass-kernels":
+SOR_PATH = "resident-kernels"
+
+
+@pytest.fixture(autouse=True, params=["resident-kernels", "mid-kernel", "pass-kernels"])
+def sor_path_switch(request, monkeypatch):
+    """By default a red-black solve takes the one-launch kernels where the grid fits them:
+    sor_small.cu (up to 12 288 cells, one SM) and sor_mid.cu (the shared memory of all SMs,
+    cooperative launch).  Every test here also runs with the small kernel off (small shapes
+    then take the mid kernel on a few CTAs) and with both off, so that all shapes keep
+    exercising the tile / streaming pass kernels."""
+    global SOR_PATH
+    SOR_PATH = request.param
+    if request.param != "resident-kernels":
         monkeypatch.setenv("SB_SOR_SMALL", "0")
+    if request.param == "pass-kernels":
+        monkeypatch.setenv("SB_SOR_MID", "0")
     yield
+    SOR_PATH = "resident-kernels"
 
 TICK = "stroemung__simulation__tests__simulation_tick"
 NORM_RTOL = 1e-12
@@ -307,7 +317,8 @@ def test_red_black_streaming_regions_match_oracle(shape, blocks, seed, T):
     n = 7
     norms = sim.sor_sweeps(n)
     slow, items = sim.rb_plan
-    assert items > 0 or blocks > 1, (slow, items)
+    if SOR_PATH == "pass-kernels":
+        assert items > 0 or blocks > 1, (slow, items)
     for k in range(n):
         o.sor_sweep()
         assert close(norms[k], o.calculate_norm_squared()), (k, norms[k])
@@ -564,6 +575,7 @@ def test_red_black_walls_and_end_rows_in_stream(shape, kinds, obstacle, T):
 
 def test_stream_kinds_env_gives_identical_fields(monkeypatch):
     """whatever subset of item kinds the streaming kernel takes, the fields are the same bits"""
+    monkeypatch.setenv("SB_SOR_MID", "0")   # this is about the pass kernels
     nx, ny = 300, 380
     kind, bu, bv = _ring(nx, ny, (1, 3, 2))
     p, u, v = random_fields(nx, ny, 5)
@@ -583,3 +595,68 @@ def test_stream_kinds_env_gives_identical_fields(monkeypatch):
             for a, b, name in zip(ref[:3], got[:3], "puv"):
                 assert_bits_equal(a, b, f"{name} with kinds {kinds}")
     assert got[3][0] < ref[3][0]          # all kinds: fewer tiles left for the tile kernel
+
+
+# ---- the grid-resident cooperative solve (sor_mid.cu) on forced decompositions ------------
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("ctas", [1, 2, 3, 7, 64, 1000])
+@pytest.mark.parametrize("shape,blocks,seed", [((257, 129), 6, 61), ((150, 300), 3, 62),
+                                               ((9, 40), 0, 63), ((331, 64), 4, 64),
+                                               ((64, 1023), 2, 65)])
+def test_mid_kernel_decompositions_match_oracle(shape, blocks, seed, ctas, variant, monkeypatch):
+    """One cooperative launch per solve, the grid split into `ctas` bands of x-rows (down to
+    2 rows per band; if a band would not fit an SM, more bands) that exchange edge rows through
+    L2 -- variant 1: generic kernel, two rows per half-sweep; variant 2: register-window
+    kernel, four rows per sweep: p bit-exact against the
+    oracle's red-black restatement whatever the decomposition, norms of every sweep within
+    the summation-order allowance, obstacles straddling band edges included; then full ticks
+    (exit rule decided on the device by every CTA alike)."""
+    if SOR_PATH != "mid-kernel":
+        pytest.skip("decompositions are forced once")
+    monkeypatch.setenv("SB_SOR_MID_CTAS", str(ctas))
+    monkeypatch.setenv("SB_SOR_MID_VARIANT", str(variant))
+    nx, ny = shape
+    kind, bu, bv = random_mask(nx, ny, seed, n_blocks=blocks)
+    p, u, v = random_fields(nx, ny, seed)
+    unf = unfinalized(nx, ny, kind, bu, bv, p=p, u=u, v=v)
+    sim = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK)
+    o = oracle_from(unf, sor_mode=po.SOR_RED_BLACK)
+    n = 9
+    launches = sim.kernel_launches
+    norms = sim.sor_sweeps(n)
+    assert sim.kernel_launches - launches == 1, "the whole solve is one launch"
+    assert sim.sor_path[0] == 1 + variant, sim.sor_path
+    for k in range(n):
+        o.sor_sweep()
+        assert close(norms[k], o.calculate_norm_squared()), (k, norms[k])
+    assert_bits_equal(sim.grid.pressure, o.p, "p after red-black sweeps")
+    for t in range(3):
+        it, nrm = sim.run_simulation_tick()
+        oit, onrm = o.run_simulation_tick()
+        assert it == oit and close(nrm, onrm), (t, it, oit, nrm, onrm)
+    assert_bits_equal(sim.grid.pressure, o.p, "p after ticks")
+    assert_bits_equal(sim.grid.u, o.u, "u after ticks")
+    assert_bits_equal(sim.grid.v, o.v, "v after ticks")
+
+
+def test_mid_kernel_early_exit():
+    """A grid of mid size whose solves end by the exit rule after 1 .. 100 sweeps (coarse
+    eps): all CTAs must leave the loop in the same sweep, and the pressure range is only
+    recomputed after a capped solve (simulation.rs:283)."""
+    if SOR_PATH == "pass-kernels":
+        pytest.skip("covers the resident kernels")
+    shape = (140, 96)
+    g = presets.simple_inflow(shape)
+    unf = unfinalized(shape[0], shape[1], g["kind"], g["bu"], g["bv"], sor_absolute_epsilon=50.0)
+    sim = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK)
+    o = oracle_from(unf, sor_mode=po.SOR_RED_BLACK)
+    seen = set()
+    for t in range(30):
+        it, nrm = sim.run_simulation_tick()
+        oit, onrm = o.run_simulation_tick()
+        assert it == oit and close(nrm, onrm), (t, it, oit, nrm, onrm)
+        seen.add(it)
+    assert len(seen) > 1, seen
+    assert_bits_equal(sim.grid.pressure, o.p, "p")
+    assert_bits_equal(sim.grid.u, o.u, "u")
+    assert list(sim.grid.pressure_range) == list(o.state().pressure_range)
