@@ -420,17 +420,14 @@ __global__ void __launch_bounds__(REG_THREADS, 1) sor_mid_reg_kernel(const MidPa
                     // y-1 / y+1 of column c: the other column of this pair or of the next pair
                     const double *yn = c == 0 ? me + REG_CPP - 1 : me - REG_CPP;
                     const double *ys = c == 0 ? me + REG_CPP : me - REG_CPP + 1;
-                    double v;
-                    switch (edge) {
-                    case SB_EDGE_N: v = *yn; break;
-                    case SB_EDGE_NE: v = (*yn + me[REG_ROWP]) / 2.0; break;
-                    case SB_EDGE_E: v = me[REG_ROWP]; break;
-                    case SB_EDGE_SE: v = (*ys + me[REG_ROWP]) / 2.0; break;
-                    case SB_EDGE_S: v = *ys; break;
-                    case SB_EDGE_SW: v = (*ys + me[-REG_ROWP]) / 2.0; break;
-                    case SB_EDGE_W: v = me[-REG_ROWP]; break;
-                    default: v = (*yn + me[-REG_ROWP]) / 2.0; break;  // SB_EDGE_NW
-                    }
+                    // branch-free: one neighbour along y, one along x, both loads in flight
+                    // (edge classes: N 1, NE 2, E 3, SE 4, S 5, SW 6, W 7, NW 8)
+                    const bool has_n = (0x106u >> edge) & 1, has_s = (0x070u >> edge) & 1;
+                    const bool has_e = (0x01cu >> edge) & 1, has_w = (0x1c0u >> edge) & 1;
+                    const double yv = *(has_n ? yn : ys);
+                    const double xv = *(has_e ? me + REG_ROWP : me - REG_ROWP);
+                    const bool has_y = has_n || has_s, has_x = has_e || has_w;
+                    const double v = (has_y && has_x) ? (yv + xv) / 2.0 : (has_y ? yv : xv);
                     *me = v;
                 }
             }
@@ -507,17 +504,39 @@ __global__ void __launch_bounds__(REG_THREADS, 1) sor_mid_reg_kernel(const MidPa
         }
         acc = warp_sum_down(acc);
         if (lane == 0) s_warp[warp] = acc;
-        __syncthreads();
-        if (tid == 0) {
-            double t = 0.0;
-            for (int w = 0; w < REG_THREADS / 32; w++) t += s_warp[w];
-            a.partial[(it & 1) * G + cta] = t;
-        }
+        __syncthreads();   // edge rows stored by all threads, warp sums in place
         MID_PHASE(3)
         arrivals += G;
-        if (!(ok = grid_barrier(a.bar, arrivals, &s_fail))) break;
+        if (warp == 0) {
+            // the CTA's sum (fixed order), then arrive: the release orders the CTA's edge rows
+            // and the sum before the arrival; one thread polls, its acquire orders the reads
+            double t = lane < REG_THREADS / 32 ? s_warp[lane] : 0.0;
+            for (int o = 8; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) {
+                a.partial[(it & 1) * G + cta] = t;
+                asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(a.bar) : "memory");
+                const long long t0 = clock64();
+                for (;;) {
+                    unsigned long long v;
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
+                    if (v >= arrivals) break;
+                    if (clock64() - t0 > (1LL << 32)) { s_fail = 1; break; }
+                }
+            }
+        }
+        __syncthreads();
+        if (s_fail) { ok = false; break; }
         MID_PHASE(4)
-        // the neighbours' edge rows -> my halo rows (mirror first, registers after the barrier)
+        // the CTAs' partial sums (warp 0; loads first, they fly with the halo loads) ...
+        double pv[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (warp == 0) {
+            const double *part = a.partial + (it & 1) * G;
+#pragma unroll
+            for (int q = 0; q < 5; q++)
+                if (32 * q + lane < G) pv[q] = __ldcg(part + 32 * q + lane);
+        }
+        // ... and the neighbours' edge rows -> my halo rows (mirror first, registers after the
+        // barrier)
         if (active) {
             double *lower = pj + lo * REG_ROWP + 1, *upper = pj + (hi - 4) * REG_ROWP + 1;
 #pragma unroll
@@ -540,19 +559,12 @@ __global__ void __launch_bounds__(REG_THREADS, 1) sor_mid_reg_kernel(const MidPa
             }
         }
         if (warp == 0) {
-            // the CTAs' partial sums, in the same order on every CTA; loads first, adds after
-            const double *part = a.partial + (it & 1) * G;
+            // same order on every CTA: identical norms, identical decisions
             double t = 0.0;
-            for (int base = 0; base < G; base += 160) {
-                double v[5];
 #pragma unroll
-                for (int q = 0; q < 5; q++) {
-                    const int i = base + 32 * q + lane;
-                    v[q] = i < G ? __ldcg(part + i) : 0.0;
-                }
-#pragma unroll
-                for (int q = 0; q < 5; q++) t += v[q];
-            }
+            for (int q = 0; q < 5; q++) t += pv[q];
+            for (int base = 160; base < G; base += 32)   // more than 160 CTAs: the rest
+                if (base + lane < G) t += __ldcg(a.partial + (it & 1) * G + base + lane);
             for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
             if (lane == 0) s_norm = t / a.fluid_cells;
         }
