@@ -676,7 +676,7 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
         // half the rows (wall_weight) and fill ~8 SMs, which on a wide grid only breaks even
         // with leaving the wall tiles to the tile kernel; up to T = 3 it wins (0.343 vs
         // 0.394 ms per pass at 8192^2).  SB_RB_STREAM_KINDS overrides (A/B runs).
-        int keep = T <= 3 ? 3 : 2;
+        int keep = 3;   // T = 4 walls too since the row-granular plan below (was: T <= 3 ? 3 : 2)
         if (const char *e = getenv("SB_RB_STREAM_KINDS")) keep = atoi(e);
         for (auto &c : cls) {
             if (!(keep & 1) && (c & 3) != 1 + IT_PLAIN) c = 0;
@@ -698,7 +698,8 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
     // runs of tiles of one item kind along x, per strip.  weight: how much longer a wall
     // strip takes per row than a plain one; its items get that much fewer rows
     struct Run { int tj, ti0, len, kind; double weight; };
-    double wall_weight = 2.0;  // measured: wall items run ~1.5-2x slower per row (see above)
+    double wall_weight = 2.0;  // measured: wall items run ~2x slower per row at T = 4 (A/B of
+                               // 1.5 / 1.7 / 2.0 in profiles/r1_stream_row_plan_ab.txt)
     if (const char *e = getenv("SB_WALL_WEIGHT")) wall_weight = atof(e);
     std::vector<Run> runs;
     std::vector<int32_t> slow;
@@ -758,14 +759,83 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
         const double cost = (double)waves * (longest * BX + 2.0 * h);
         if (cost < best_cost) { best_cost = cost; best_seg = seg; }
     }
+    // Row-granular plan for ONE wave: split the resident CTAs between the two kinds, hand the
+    // item slots of a kind to its runs one by one (always to the run whose pieces are longest)
+    // and cut every run into equal pieces at arbitrary (even) rows.  The tile-granular search
+    // above can only cut at tile rows and wastes up to a tile per item: with the two wall
+    // strips of an 8192^2 channel in the stream it ended 12 % above the ideal and only broke
+    // even with leaving them to the tile kernel; this one ends 5 % above (the walls' share).
+    auto run_rows = [&](const Run &r) {
+        const int64_t a = g.own0 + (int64_t)r.ti0 * BX;
+        return (int)(std::min<int64_t>(a + (int64_t)r.len * BX, g.own1) - a);
+    };
+    std::vector<int> row_pieces;   // pieces per run; empty = keep the tile-granular plan
+    {
+        const char *e = getenv("SB_RB_ROW_PLAN");
+        const bool enabled = !(e && atoi(e) == 0);
+        int nrun[2] = {0, 0};
+        for (const Run &r : runs) nrun[r.kind != IT_PLAIN]++;
+        double best = best_cost;
+        for (int64_t cw = 0; enabled && cw <= resident; cw++) {
+            const int64_t c_k[2] = {resident - cw, cw};
+            if ((nrun[0] > 0) != (c_k[0] > 0) && nrun[0] > 0) continue;
+            if ((nrun[1] > 0) != (c_k[1] > 0)) continue;
+            if (c_k[0] * nwarp < nrun[0] || c_k[1] * nwarp < nrun[1]) continue;
+            std::vector<int> m(runs.size(), 1);
+            double cost = 0.0;
+            for (int k = 0; k < 2; k++) {
+                int64_t spare = c_k[k] * nwarp - nrun[k];
+                // (piece length, run) max-heap
+                std::vector<std::pair<double, int>> heap;
+                for (size_t i = 0; i < runs.size(); i++)
+                    if ((runs[i].kind != IT_PLAIN) == (k == 1))
+                        heap.push_back({(double)run_rows(runs[i]), (int)i});
+                std::make_heap(heap.begin(), heap.end());
+                while (spare > 0 && !heap.empty()) {
+                    std::pop_heap(heap.begin(), heap.end());
+                    auto top = heap.back();
+                    heap.pop_back();
+                    const int i = top.second, rows = run_rows(runs[i]);
+                    if (rows / (m[i] + 1) < BX) {   // pieces shorter than a tile: not worth it
+                        heap.push_back({0.0, i});
+                        std::push_heap(heap.begin(), heap.end());
+                        if (top.first == 0.0) break;
+                        continue;
+                    }
+                    m[i]++;
+                    spare--;
+                    heap.push_back({(double)rows / m[i], i});
+                    std::push_heap(heap.begin(), heap.end());
+                }
+                for (size_t i = 0; i < runs.size(); i++)
+                    if ((runs[i].kind != IT_PLAIN) == (k == 1))
+                        cost = std::max(cost, ((run_rows(runs[i]) + m[i] - 1) / m[i] + 2.0 * h) *
+                                                  runs[i].weight);
+            }
+            if (cost < best) {
+                best = cost;
+                row_pieces = m;
+            }
+        }
+    }
     std::vector<RbItem> by_kind[2];  // plain strips / wall strips: one copy of the code each
-    for (const Run &r : runs) {
-        const int m = pieces(r, best_seg);
+    for (size_t ri = 0; ri < runs.size(); ri++) {
+        const Run &r = runs[ri];
+        const bool by_rows = !row_pieces.empty();
+        const int m = by_rows ? row_pieces[ri] : pieces(r, best_seg);
+        const int64_t rx0 = g.own0 + (int64_t)r.ti0 * BX, rrows = run_rows(r);
         for (int i = 0; i < m; i++) {
             const int a = (int)((int64_t)r.len * i / m), b = (int)((int64_t)r.len * (i + 1) / m);
             RbItem it;
-            it.x0 = (int32_t)(g.own0 + (int64_t)(r.ti0 + a) * BX);
-            it.x1 = (int32_t)std::min<int64_t>(g.own0 + (int64_t)(r.ti0 + b) * BX, g.own1);
+            if (by_rows) {
+                const int64_t ra = i == 0 ? 0 : (rrows * i / m) & ~(int64_t)1;
+                const int64_t rb = i == m - 1 ? rrows : (rrows * (i + 1) / m) & ~(int64_t)1;
+                it.x0 = (int32_t)(rx0 + ra);
+                it.x1 = (int32_t)(rx0 + rb);
+            } else {
+                it.x0 = (int32_t)(g.own0 + (int64_t)(r.ti0 + a) * BX);
+                it.x1 = (int32_t)std::min<int64_t>(g.own0 + (int64_t)(r.ti0 + b) * BX, g.own1);
+            }
             int flags = r.kind, st0 = h, st1 = SW - h;
             it.ty0 = r.tj * BY - h;
             if (r.kind == IT_WALL_LO) { it.ty0 = 0; st0 = 0; st1 = BY; }
@@ -774,8 +844,9 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
                 st0 = r.tj * BY - it.ty0;
                 st1 = SW;
             }
-            if (cls[(size_t)(r.ti0 + a) * tiles_y + r.tj] & TC_BC_LO) flags |= IT_BC_LO;
-            if (cls[(size_t)(r.ti0 + b - 1) * tiles_y + r.tj] & TC_BC_HI) flags |= IT_BC_HI;
+            const int ta = by_rows ? (i == 0 ? 0 : -1) : a, tb = by_rows ? (i == m - 1 ? r.len : -1) : b;
+            if (ta >= 0 && (cls[(size_t)(r.ti0 + ta) * tiles_y + r.tj] & TC_BC_LO)) flags |= IT_BC_LO;
+            if (tb >= 1 && (cls[(size_t)(r.ti0 + tb - 1) * tiles_y + r.tj] & TC_BC_HI)) flags |= IT_BC_HI;
             it.pad = flags | (st0 << 8) | (st1 << 16);
             by_kind[r.kind != IT_PLAIN].push_back(it);
         }
