@@ -360,6 +360,7 @@ def run_ours(args):
                 "dram_gbs": traffic / (avg_ms * 1e-3) / 1e9 if traffic else None,
                 "peak_source": peak_src, "launches_timed": len(work),
                 "avg_launch_ms": avg_ms, "sweeps_per_launch": sweeps_per_launch,
+                "launch_ms_min_median_max": [min(work), statistics.median(work), max(work)],
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "achieved = 25 B per cell-sweep x cells x sweeps per pass / pass time "
                         "(CUDA events around every pass of the timed region); a pass fuses T "

@@ -493,7 +493,14 @@ sb_status sb_create_preset(const sb_params *params, int32_t preset, const double
     return SB_OK;
 }
 
-void sb_destroy(sb_sim *sim) { destroy(sim); }
+void sb_destroy(sb_sim *sim) {
+    if (sim && sim->slab && getenv("SB_FIN_TRACE")) {
+        cudaSetDevice(sim->device);
+        cudaStreamSynchronize(sim->stream);
+        sb::dump_finalize_trace(sim->link.rank);
+    }
+    destroy(sim);
+}
 
 sb_status sb_tick(sb_sim *sim, uint32_t *sor_iterations, double *norm_squared) {
     SB_ENTER(sim);

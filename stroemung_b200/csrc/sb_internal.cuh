@@ -252,6 +252,7 @@ sb_status launch_sor_finalize(sb_sim *s, int nparts, double initial_norm, double
 // d_scalars[0] = (sum of partial[0..n)) / fluid_cells, read back into *out
 sb_status reduce_norm(sb_sim *s, int nparts, double *out);
 sb_status restore_edges_from_list(sb_sim *s);
+void dump_finalize_trace(int rank);   // SB_FIN_TRACE
 sb_status launch_mark_valid(sb_sim *s, const uint8_t *d_kind_rows, int keep_edges);
 sb_status launch_preset(sb_sim *s, int preset, const double *args);
 sb_status launch_edit_block(sb_sim *s, int64_t gx, int64_t gy, uint8_t kind, double *backup,

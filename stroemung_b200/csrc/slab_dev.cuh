@@ -31,6 +31,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_relaxed_sys_f64(double *p, double v) {
     asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
@@ -62,18 +67,20 @@ __device__ __forceinline__ bool slab_allgather(const SlabLink &lk, const double 
     if (t < lk.world) {
         MailSlot *dst = lk.mbox[t] + (round & 1) * SB_MAX_WORLD + lk.rank;
         for (int i = 0; i < n; i++) st_relaxed_sys_f64(&dst->vals[i], my_vals[i]);
-        __threadfence_system();
+        // the release store orders the values (and this thread's earlier stores) before the
+        // flag by itself: no separate fence in front of it
         st_release_sys_u64(&dst->seq, round);
         const MailSlot *src = lk.mbox[lk.rank] + (round & 1) * SB_MAX_WORLD + t;
         const long long t0 = clock64();
         bool ok = true;
-        while (ld_acquire_sys_u64(&src->seq) != round) {
+        // relaxed polls, one acquire fence once the flag is there
+        while (ld_relaxed_sys_u64(&src->seq) != round) {
             if (clock64() - t0 > SLAB_WAIT_CLOCKS) {
                 ok = false;
                 break;
             }
-            __nanosleep(64);
         }
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
         if (ok) {
             for (int i = 0; i < n; i++) gathered[t * 8 + i] = ld_relaxed_sys_f64(&src->vals[i]);
         } else {

@@ -43,6 +43,7 @@
 // What kind of item a lattice tile can join is decided per tile by rb_class_kernel; the host
 // turns runs of equal tiles along x into work items (RbPlan).  Everything else -- obstacles,
 // corners of walls, slab edges -- stays with the tile kernel.
+#include <limits.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -133,6 +134,18 @@ struct SCtx {
     const double *pl, *rl;     // this lane's pair A in slot 0 of the p / rhs ring
     uint64_t *bar;
     RbConsts k;
+};
+
+// What the streaming kernel needs to know about the neighbouring slabs (SlabLink, slab.cu).
+// Row slabs: the rows within H of a slab edge are also stored into the neighbour's halo rows
+// of ITS target buffer (P2P over NVLink).  Lives in the kernel's parameter space (constant
+// bank) and is only touched on the warm-up / drain path: no registers in the steady loop.
+struct StreamPeers {
+    double *lo_p[2], *hi_p[2];   // the neighbours' two pressure buffers (nullptr: none)
+    int64_t lo_row0, hi_row0;    // local row of THEIR array that receives my first / last H rows
+    int own0, own1, H;
+    double *const *pbuf;         // my own two buffers and the control block (for src)
+    const SorCtl *ctl;
 };
 
 // request row `row` (both arrays) into rhs slot `slot` / p slot `slot % NP`; lane 0 only
@@ -269,7 +282,7 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
                                             double (&FR)[2][2], double (&accA)[T],
                                             double (&accB)[T], const int U, const int R,
                                             const int64_t roff, const uint32_t ph,
-                                            const SCtx &c) {
+                                            const SCtx &c, const StreamPeers &pe) {
     constexpr int NW = stream_nw(T), NP = stream_np(T), PF = stream_pf(T);
     const RbConsts &k = c.k;
     // ---- request row R + PF; row R: shared-memory ring -> registers ------------------------
@@ -361,13 +374,29 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
             double *dst = c.pout + (roff - lag * c.pitch);
             if (c.cmA) stg_f64x2(dst, W[s][0], W[s][1]);
             if (c.cmB) stg_f64x2(dst + 64, W[s][2], W[s][3]);
+            // halo exchange fused into the pass: the rows within H of a slab edge also go
+            // straight into the neighbour's halo rows (the steady range keeps clear of them)
+            if (!STEADY) {
+                const bool to_lo = pe.lo_p[0] != nullptr && q < pe.own0 + pe.H;
+                const bool to_hi = pe.hi_p[0] != nullptr && q >= pe.own1 - pe.H;
+                if (to_lo || to_hi) {  // warp-uniform, rare: 2H rows per slab and strip
+                    const int dstbuf = pe.ctl->src ^ 1;
+                    const int64_t rowshift = to_lo ? pe.lo_row0 - pe.own0
+                                                   : pe.hi_row0 - (pe.own1 - pe.H);
+                    double *peer = (to_lo ? pe.lo_p[dstbuf] : pe.hi_p[dstbuf]) +
+                                   (dst - pe.pbuf[dstbuf]) + rowshift * c.pitch;
+                    if (c.cmA) stg_f64x2(peer, W[s][0], W[s][1]);
+                    if (c.cmB) stg_f64x2(peer + 64, W[s][2], W[s][3]);
+                }
+            }
         }
     }
 }
 
 template <int T, int WALL>
 __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
-                                            double *__restrict__ partial, int64_t part_stride) {
+                                            double *__restrict__ partial, int64_t part_stride,
+                                            const StreamPeers &pe) {
     constexpr int NW = stream_nw(T), NP = stream_np(T), PF = stream_pf(T);
     constexpr int HP = 2 * T + 2;
     const bool lo = flags & IT_BC_LO, hi = flags & IT_BC_HI;
@@ -384,8 +413,11 @@ __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
     const int rs = c.first - ((gpar + c.first) & 1);
     // steady ticks R in [st_lo, st_hi]: rows R-1 .. R-(2T+2) are ordinary counted rows (not
     // next to a boundary row either) and row R + PF is still to be requested
-    const int st_lo = c.x0 + (lo ? 2 : 0) + 2 * T + 2;
-    const int st_hi = min(c.x1 - (hi ? 2 : 0), c.re - PF - 1);
+    // (a steady tick R retires row R - (2T+2) without tests: not a row a neighbour slab gets)
+    const int lo_end = pe.lo_p[0] != nullptr ? pe.own0 + pe.H : INT_MIN;
+    const int hi_beg = pe.hi_p[0] != nullptr ? pe.own1 - pe.H : INT_MAX - 64;
+    const int st_lo = max(c.x0 + (lo ? 2 : 0), lo_end) + 2 * T + 2;
+    const int st_hi = min(min(c.x1 - (hi ? 2 : 0), c.re - PF - 1), hi_beg + 2 * T + 1);
     if (c.lane == 0) {
         for (int i = 0; i < NW; i++) mbar_init(c.bar + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -409,7 +441,7 @@ __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
             do {  // the steady state: straight-line code, no row tests
 #pragma unroll
                 for (int U = 0; U < NW; U++) {
-                    stream_tick<T, true, WALL>(W, C, FR, accA, accB, U, R0 + U, roff, ph, c);
+                    stream_tick<T, true, WALL>(W, C, FR, accA, accB, U, R0 + U, roff, ph, c, pe);
                     roff += c.pitch;
                 }
                 ph ^= 1u;
@@ -421,7 +453,7 @@ __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
 #pragma unroll
             for (int U = 0; U < NW; U++) {
                 if (R0 + U >= c.rend) break;
-                stream_tick<T, false, WALL>(W, C, FR, accA, accB, U, R0 + U, roff, ph, c);
+                stream_tick<T, false, WALL>(W, C, FR, accA, accB, U, R0 + U, roff, ph, c, pe);
                 roff += c.pitch;
             }
             ph ^= 1u;
@@ -437,9 +469,9 @@ __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
 
 template <int T>
 __device__ __forceinline__ void stream_item_any(SCtx &c, int flags, int gpar, double *partial,
-                                                int64_t part_stride) {
-    if ((flags & 3) == IT_PLAIN) stream_item<T, 0>(c, flags, gpar, partial, part_stride);
-    else stream_item<T, 1>(c, flags, gpar, partial, part_stride);
+                                                int64_t part_stride, const StreamPeers &pe) {
+    if ((flags & 3) == IT_PLAIN) stream_item<T, 0>(c, flags, gpar, partial, part_stride, pe);
+    else stream_item<T, 1>(c, flags, gpar, partial, part_stride, pe);
 }
 
 // one work item per warp, stream_warps(TB) warps per CTA, one CTA per SM; TB = the configured
@@ -449,7 +481,8 @@ template <int TB>
 __global__ void __launch_bounds__(32 * stream_warps(TB), 1)
 sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict__ pbuf,
                      const double *__restrict__ rhs, SorCtl *ctl, double *partial, int part_base,
-                     int part_stride, int64_t pitch, int gpar, RbConsts k, RbFin fin) {
+                     int part_stride, int64_t pitch, int gpar, RbConsts k, RbFin fin,
+                     const __grid_constant__ StreamPeers pe) {
     const int T = ctl->active_T;
     if (T == 0) return;
     const int src = ctl->src;
@@ -482,6 +515,7 @@ sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict
     c.x0 = it.x0;
     c.x1 = it.x1;
     c.k = k;
+
     // stored = counted columns [st0, st1) of the strip (pair-aligned; a wall cell inside is
     // stored but not counted: keepA / keepB)
     c.cmA = 2 * c.lane >= st0 && 2 * c.lane < st1;
@@ -496,10 +530,10 @@ sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict
         g_trace[4 * idx + 2] = smid;
         g_trace[4 * idx + 3] = (unsigned)flags | ((unsigned long long)(it.x1 - it.x0) << 8);
     }
-    if (T == TB) stream_item_any<TB>(c, flags, gpar, part, part_stride);
-    else if (TB > 1 && T == 1) stream_item_any<1>(c, flags, gpar, part, part_stride);
-    else if (TB > 2 && T == 2) stream_item_any<2>(c, flags, gpar, part, part_stride);
-    else if (TB > 3 && T == 3) stream_item_any<3>(c, flags, gpar, part, part_stride);
+    if (T == TB) stream_item_any<TB>(c, flags, gpar, part, part_stride, pe);
+    else if (TB > 1 && T == 1) stream_item_any<1>(c, flags, gpar, part, part_stride, pe);
+    else if (TB > 2 && T == 2) stream_item_any<2>(c, flags, gpar, part, part_stride, pe);
+    else if (TB > 3 && T == 3) stream_item_any<3>(c, flags, gpar, part, part_stride, pe);
     if (trace && c.lane == 0) g_trace[4 * idx + 1] = gtime();
     }
     // ---- the last CTA to finish totals the partials of the whole pass (tile kernel's
@@ -536,7 +570,7 @@ sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict
 }
 
 using StreamKernel = void (*)(const RbItem *, double *const *, const double *, SorCtl *,
-                              double *, int, int, int64_t, int, RbConsts, RbFin);
+                              double *, int, int, int64_t, int, RbConsts, RbFin, StreamPeers);
 StreamKernel stream_kernel(int TB) {
     switch (TB) {
     case 1: return sor_rb_stream_kernel<1>;
@@ -683,9 +717,11 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
             if (!(keep & 2) && (c & (TC_BC_LO | TC_BC_HI))) c = 0;
         }
     }
-    if (s->slab) {
-        // tiles that own rows within H of a slab edge also feed the neighbour's halo rows:
-        // that code lives in the tile kernel
+    const char *edge_env = getenv("SB_SLAB_EDGE_TILES");
+    if (s->slab && edge_env && atoi(edge_env) == 1) {
+        // A/B: tiles that own rows within H of a slab edge on the tile kernel (its epilogue
+        // feeds the neighbour's halo rows too).  Default: the streaming kernel stores those
+        // rows into the neighbour's halo itself, and a plain channel needs no tile kernel
         const int H = s->link.H;
         for (int ti = 0; ti < tiles_x; ti++) {
             const int64_t x0 = g.own0 + (int64_t)ti * BX, x1 = std::min<int64_t>(x0 + BX, g.own1);
@@ -912,6 +948,15 @@ sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h,
         }
         fin.counter = s->plan.d_counter;
     }
+    StreamPeers pe{};
+    if (s->slab) {
+        pe.lo_p[0] = s->link.lo_p[0]; pe.lo_p[1] = s->link.lo_p[1];
+        pe.hi_p[0] = s->link.hi_p[0]; pe.hi_p[1] = s->link.hi_p[1];
+        pe.lo_row0 = s->link.lo_row0; pe.hi_row0 = s->link.hi_row0;
+        pe.own0 = (int)g.own0; pe.own1 = (int)g.own1; pe.H = s->link.H;
+    }
+    pe.pbuf = rb_pbuf_ptr(s);
+    pe.ctl = s->d_ctl;
     static int trace_set = 0;
     if (!trace_set && getenv("SB_STREAM_TRACE")) {
         const int one = 1;
@@ -920,7 +965,7 @@ sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h,
     }
     stream_kernel(TB)<<<s->plan.n_items / nw, 32 * nw, stream_smem_bytes(TB), s->stream>>>(
         s->plan.d_items, rb_pbuf_ptr(s), s->rhs, s->d_ctl, s->d_partial, part_base, part_stride,
-        g.pitch, gpar, rb_consts(s), fin);
+        g.pitch, gpar, rb_consts(s), fin, pe);
     s->launches++;
     SB_CUDA(cudaGetLastError());
     return SB_OK;

@@ -397,6 +397,17 @@ __global__ void norm_partial_kernel(Geom g, double *const *__restrict__ pbuf,
 //     norm < initial_norm || norm < eps^2   -> stop after this sweep.
 // A red-black pass runs T sweeps speculatively; if the rule fires at level k < T the pass
 // is repeated from the same source buffer with T = k (deterministic, so it then ends at k).
+// SB_FIN_TRACE: where a slab-mode finalize spends its time (globaltimer ns, this device):
+// [0] launches, [1] inside the kernel, [2] of that inside the all-gather, [3] end of the last
+// one, [4] from the end of one to the start of the next (= the pass in between, launch gaps
+// included)
+__device__ unsigned long long g_fin_trace[8];
+__device__ __forceinline__ unsigned long long fin_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void sor_finalize_kernel(SorCtl *__restrict__ ctl, const double *__restrict__ partial,
                                     int nparts, double fluid_cells, double initial_norm,
                                     double eps2, int test_exit, double *__restrict__ norm_hist,
@@ -407,6 +418,8 @@ __global__ void sor_finalize_kernel(SorCtl *__restrict__ ctl, const double *__re
     __shared__ double gathered[SB_MAX_WORLD * 8];
     int T = ctl->active_T;
     if (T == 0) return;
+    const unsigned long long tr0 = fin_gtime();
+    unsigned long long tr1 = tr0, tr2 = tr0;
     for (int lvl = 0; lvl < T; lvl++) {
         double acc = 0.0;
         for (int i = threadIdx.x; i < nparts; i += blockDim.x)
@@ -424,7 +437,10 @@ __global__ void sor_finalize_kernel(SorCtl *__restrict__ ctl, const double *__re
     if (lk.world > 1) {
         // row slabs: every rank sums the per-slab totals in rank order -> identical norms and
         // identical exit decisions on all GPUs, no host in the loop (slab_dev.cuh)
-        if (!slab_allgather(lk, level_sum, T, gathered)) {
+        tr1 = fin_gtime();
+        const bool gathered_ok = slab_allgather(lk, level_sum, T, gathered);
+        tr2 = fin_gtime();
+        if (!gathered_ok) {
             if (threadIdx.x == 0) {  // a peer went missing: end the solve, the host reports it
                 ctl->active_T = 0;
                 ctl->finished = 1;
@@ -442,7 +458,15 @@ __global__ void sor_finalize_kernel(SorCtl *__restrict__ ctl, const double *__re
     __syncthreads();
     if (threadIdx.x != 0) return;
     sor_advance_ctl(ctl, level_norm, T, initial_norm, eps2, test_exit, norm_hist);
+    const unsigned long long tr3 = fin_gtime();
+    g_fin_trace[0] += 1;
+    g_fin_trace[1] += tr3 - tr0;
+    g_fin_trace[2] += tr2 - tr1;
+    if (g_fin_trace[3] && tr0 - g_fin_trace[3] < 100000000ull) g_fin_trace[4] += tr0 - g_fin_trace[3];
+    g_fin_trace[3] = tr3;
 }
+
+
 
 // out[0] = (sum of partial[0..n)) / fluid_cells, same tree as the finalize kernel
 __global__ void sum_partials_kernel(const double *__restrict__ partial, int nparts,
@@ -655,6 +679,14 @@ sb_status ensure_partial(sb_sim *s, size_t need) {
 }
 
 }  // namespace
+
+void dump_finalize_trace(int rank) {
+    unsigned long long h[8];
+    if (cudaMemcpyFromSymbol(h, g_fin_trace, sizeof(h)) != cudaSuccess || !h[0]) return;
+    fprintf(stderr, "[sb finalize trace] rank %d: %llu finalize launches, %.1f us in the kernel "
+            "(%.1f us of it in the all-gather), %.1f us from the end of one to the start of the "
+            "next\n", rank, h[0], h[1] / 1e3 / h[0], h[2] / 1e3 / h[0], h[4] / 1e3 / h[0]);
+}
 
 // device array of the two pressure buffer pointers lives right after the ctl block
 static double *const *pbuf_ptr(sb_sim *s) {
