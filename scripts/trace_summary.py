@@ -6,7 +6,7 @@ import sys
 
 rows = []
 for l in open(sys.argv[1]):
-    m = re.match(r"\[sb trace\] item (\d+) kind (\d) flags (\d+) rows (\d+) sm (\d+) start ([\d.]+) us dur ([\d.]+) us", l)
+    m = re.match(r"\[sb trace\] (?:rank \d+ )?item (\d+) kind (\d) flags (\d+) rows (\d+) sm (\d+) start ([\d.]+) us dur ([\d.]+) us", l)
     if m:
         rows.append(tuple(float(x) for x in m.groups()))
 nw = int(sys.argv[2]) if len(sys.argv) > 2 else 8

@@ -132,6 +132,16 @@ static sb_status allocate(const sb_params *params, sb_sim **out) {
     g.own0 = s->halo;
     g.own1 = s->halo + (xe - xb);
     g.pitch = round_up(g.NY, 16);
+    {
+        // Experiment knob (default off): SB_PITCH_PAD=n adds n elements to a row pitch that is a
+        // multiple of 2 KB.  The wall strips of a channel run 1.5-2.5x slower per row than a
+        // plain strip and all their warps advance in lockstep (per-item trace) -- which looks
+        // like all rows of a strip queueing on a few HBM channels -- but padding the pitch by
+        // 128 B .. 8 KB did not change that (profiles/r1_wall_strip_experiments.txt).
+        const char *e = getenv("SB_PITCH_PAD");
+        const int pad = e ? atoi(e) : 0;
+        if (pad > 0 && (g.pitch * (int64_t)sizeof(double)) % 2048 == 0) g.pitch += round_up(pad, 16);
+    }
     s->field_bytes = (size_t)g.nxl * g.pitch * sizeof(double);
     s->flag_bytes = (size_t)g.nxl * g.pitch;
 #define SB_TRY(call)                                                            \

@@ -659,9 +659,9 @@ static void dump_trace(sb_sim *s) {
         if (t[4 * i + 1]) t0 = std::min(t0, t[4 * i]);
     for (int i = 0; i < n; i++) {
         if (!t[4 * i + 1]) continue;
-        fprintf(stderr, "[sb trace] item %d kind %d flags %d rows %d sm %d start %.1f us dur %.1f us"
+        fprintf(stderr, "[sb trace] rank %d item %d kind %d flags %d rows %d sm %d start %.1f us dur %.1f us"
                 " warmup %.1f steady %.1f drain %.1f\n",
-                i, (int)(t[4 * i + 3] & 3), (int)(t[4 * i + 3] & 0xff), (int)(t[4 * i + 3] >> 8),
+                s->slab ? s->link.rank : 0, i, (int)(t[4 * i + 3] & 3), (int)(t[4 * i + 3] & 0xff), (int)(t[4 * i + 3] >> 8),
                 (int)t[4 * i + 2], (t[4 * i] - t0) * 1e-3, (t[4 * i + 1] - t[4 * i]) * 1e-3,
                 (t2[2 * i] - t[4 * i]) * 1e-3, (t2[2 * i + 1] - t2[2 * i]) * 1e-3,
                 (t[4 * i + 1] - t2[2 * i + 1]) * 1e-3);
@@ -734,8 +734,13 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
     // runs of tiles of one item kind along x, per strip.  weight: how much longer a wall
     // strip takes per row than a plain one; its items get that much fewer rows
     struct Run { int tj, ti0, len, kind; double weight; };
-    double wall_weight = 2.0;  // measured: wall items run ~2x slower per row at T = 4 (A/B of
-                               // 1.5 / 1.7 / 2.0 in profiles/r1_stream_row_plan_ab.txt)
+    // Wall items run 1.5x (one GPU) to 2.5x (a slab with a neighbour in front) slower per row
+    // than plain ones AND their total throughput hardly grows with the number of warps on
+    // them (per-item traces, profiles/r1_wall_strip_experiments.txt): they must start with
+    // plenty of warps and never be the straggler.  The pass as a whole is bandwidth-bound, so
+    // the plain items do not care about the SMs that takes away: weight 6 is as fast as 2 on
+    // one GPU (12.34 vs 12.40 ms per tick at 8192^2) and 11 % faster on two slabs.
+    double wall_weight = 6.0;
     if (const char *e = getenv("SB_WALL_WEIGHT")) wall_weight = atof(e);
     std::vector<Run> runs;
     std::vector<int32_t> slow;
