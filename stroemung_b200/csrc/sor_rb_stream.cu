@@ -817,15 +817,18 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
         int nrun[2] = {0, 0};
         for (const Run &r : runs) nrun[r.kind != IT_PLAIN]++;
         double best = best_cost;
-        for (int64_t cw = 0; enabled && cw <= resident; cw++) {
+        // waves: grids with many strips (32768 columns: 304 runs for 1184 slots) balance better
+        // with two to four rounds of shorter items than with one round of 3 or 4 per strip
+        for (int waves = 1; enabled && waves <= 6; waves++)
+        for (int64_t cw = 0; cw <= resident; cw++) {
             const int64_t c_k[2] = {resident - cw, cw};
             if ((nrun[0] > 0) != (c_k[0] > 0) && nrun[0] > 0) continue;
             if ((nrun[1] > 0) != (c_k[1] > 0)) continue;
-            if (c_k[0] * nwarp < nrun[0] || c_k[1] * nwarp < nrun[1]) continue;
+            if (c_k[0] * nwarp * waves < nrun[0] || c_k[1] * nwarp * waves < nrun[1]) continue;
             std::vector<int> m(runs.size(), 1);
             double cost = 0.0;
             for (int k = 0; k < 2; k++) {
-                int64_t spare = c_k[k] * nwarp - nrun[k];
+                int64_t spare = c_k[k] * nwarp * waves - nrun[k];
                 // (piece length, run) max-heap
                 std::vector<std::pair<double, int>> heap;
                 for (size_t i = 0; i < runs.size(); i++)
@@ -850,9 +853,10 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
                 }
                 for (size_t i = 0; i < runs.size(); i++)
                     if ((runs[i].kind != IT_PLAIN) == (k == 1))
-                        cost = std::max(cost, ((run_rows(runs[i]) + m[i] - 1) / m[i] + 2.0 * h) *
+                        cost = std::max(cost, waves * ((run_rows(runs[i]) + m[i] - 1) / m[i] + 2.0 * h) *
                                                   runs[i].weight);
             }
+            cost *= 1.0 + 0.03 * (waves - 1);   // ties go to fewer, longer items
             if (cost < best) {
                 best = cost;
                 row_pieces = m;
