@@ -735,12 +735,13 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
     // strip takes per row than a plain one; its items get that much fewer rows
     struct Run { int tj, ti0, len, kind; double weight; };
     // Wall items run 1.5x (one GPU) to 2.5x (a slab with a neighbour in front) slower per row
-    // than plain ones AND their total throughput hardly grows with the number of warps on
-    // them (per-item traces, profiles/r1_wall_strip_experiments.txt): they must start with
-    // plenty of warps and never be the straggler.  The pass as a whole is bandwidth-bound, so
-    // the plain items do not care about the SMs that takes away: weight 6 is as fast as 2 on
-    // one GPU (12.34 vs 12.40 ms per tick at 8192^2) and 11 % faster on two slabs.
-    double wall_weight = 6.0;
+    // than plain ones, and in a slab their total throughput hardly grows with the number of
+    // warps on them (per-item traces, profiles/r1_wall_strip_experiments.txt): there they must
+    // start with plenty of warps or they are the straggler every pass (weight 6: two slabs
+    // 14.7 -> 13.1 ms per tick).  On one GPU weight 2 balances them; a larger weight costs
+    // nothing on a wide grid (8192^2: 12.34 vs 12.40 ms) but 15 % on a narrow one (8192 x 2048:
+    // 2 of 19 strips are walls), so it stays at 2 there.
+    double wall_weight = s->slab ? 6.0 : 2.0;
     if (const char *e = getenv("SB_WALL_WEIGHT")) wall_weight = atof(e);
     std::vector<Run> runs;
     std::vector<int32_t> slow;
