@@ -318,13 +318,20 @@ static sb_status solve(sb_sim *s, uint32_t max_it, int test_exit, uint32_t *iter
     uint32_t hint = s->sor_batch_hint ? s->sor_batch_hint : 4;
     uint32_t enq = 0;
     const bool small = rb && max_it > 0 && sor_small_fits(s);
-    const bool mid = rb && max_it > 0 && !small && sor_mid_fits(s);
+    bool mid = rb && max_it > 0 && !small && !s->mid_unavailable && sor_mid_fits(s);
+    if (mid) {
+        // a cooperative launch needs all its CTAs resident at once; where the device cannot
+        // promise that (SMs taken by another context) the pass kernels take the solve
+        st = launch_sor_mid(s, init, eps2, test_exit, d_hist);
+        if (st == SB_OK && s->mid_unavailable) mid = false;
+        else if (st) return st;
+    }
     if (small || mid) {  // the whole solve in one launch (sor_small.cu / sor_mid.cu)
-        s->last_sor_path = small ? 1 : 2;
-        s->last_sor_ctas = 1;
-        if (small) st = launch_sor_small(s, init, eps2, test_exit, d_hist);
-        else st = launch_sor_mid(s, init, eps2, test_exit, d_hist);
-        if (st) return st;
+        if (small) {
+            s->last_sor_path = 1;
+            s->last_sor_ctas = 1;
+            if ((st = launch_sor_small(s, init, eps2, test_exit, d_hist))) return st;
+        }
         SB_CUDA(cudaMemcpyAsync(h, s->d_ctl, sizeof(SorCtl), cudaMemcpyDeviceToHost, s->stream));
         SB_CUDA(cudaStreamSynchronize(s->stream));
         if (h->pad) {

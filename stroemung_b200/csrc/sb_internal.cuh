@@ -196,6 +196,7 @@ struct sb_sim {
     void *d_mid = nullptr;                    // sor_mid.cu: barrier word, exchange rows, partials
     size_t mid_cap = 0;
     int last_sor_path = 0, last_sor_ctas = 0;  // sb_last_sor_path
+    bool mid_unavailable = false;             // a cooperative launch was refused on this device
     uchar4 *d_img = nullptr;                  // RGBA8 frame of sb_render_rgba (lazy)
     // tensor maps for the red-black pass (built lazily per buffer)
     bool tmaps_ready = false;

@@ -688,8 +688,14 @@ sb_status launch_reg(const MidPlan &pl, MidParams &a, int smem_optin, cudaStream
         attr_set[dev & 63] = true;
     }
     void *args[] = {&a};
-    SB_CUDA(cudaLaunchCooperativeKernel((const void *)sor_mid_reg_kernel<RM>, dim3(pl.ctas),
-                                        dim3(REG_THREADS), args, pl.smem, stream));
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)sor_mid_reg_kernel<RM>,
+                                                      dim3(pl.ctas), dim3(REG_THREADS), args,
+                                                      pl.smem, stream);
+    if (e == cudaErrorCooperativeLaunchTooLarge) {
+        cudaGetLastError();
+        return SB_INVALID_ARGUMENT;   // "not now": the caller falls back to the pass kernels
+    }
+    SB_CUDA(e);
     return SB_OK;
 }
 
@@ -757,11 +763,23 @@ sb_status launch_sor_mid(sb_sim *s, double initial_norm, double eps2, int test_e
         else if (pl.rmax == 6) st = launch_reg<6>(pl, a, d.smem_optin, s->stream);
         else if (pl.rmax == 7) st = launch_reg<7>(pl, a, d.smem_optin, s->stream);
         else st = launch_reg<8>(pl, a, d.smem_optin, s->stream);
-        if (st) return st;
     } else {
-        SB_CUDA(cudaLaunchCooperativeKernel((const void *)sor_mid_kernel, dim3(pl.ctas),
-                                            dim3(MID_THREADS), args, pl.smem, s->stream));
+        const cudaError_t e = cudaLaunchCooperativeKernel((const void *)sor_mid_kernel,
+                                                          dim3(pl.ctas), dim3(MID_THREADS), args,
+                                                          pl.smem, s->stream);
+        if (e == cudaErrorCooperativeLaunchTooLarge) {
+            cudaGetLastError();
+            st = SB_INVALID_ARGUMENT;
+        } else {
+            SB_CUDA(e);
+        }
     }
+    if (st == SB_INVALID_ARGUMENT) {  // not all CTAs can be resident here: never try again
+        s->mid_unavailable = true;
+        prof_mark(s);   // closes the pair opened above (an empty entry)
+        return SB_OK;
+    }
+    if (st) return st;
     s->launches++;
     s->last_sor_ctas = pl.ctas;
     s->last_sor_path = pl.variant == 2 ? 3 : 2;
