@@ -282,6 +282,7 @@ static sb_status solve(sb_sim *s, uint32_t max_it, int test_exit, uint32_t *iter
         }
         d_hist = s->d_hist;
     }
+    s->solve_seq++;
     SB_CUDA(cudaEventRecord(s->ev_sor0, s->stream));
     if (max_it == 0 || s->g.NX < 3 || s->g.NY < 3) {
         // no interior: the sweep and the norm are empty loops (0.0 / fluid_cells)

@@ -113,6 +113,16 @@ struct RbPlan {
     uint8_t *d_plain = nullptr;  // scratch: one byte per tile
     unsigned *d_counter = nullptr;  // CTAs of the streaming kernel done (fused finalize)
     size_t cap_tiles = 0, cap_items = 0;
+    // "frozen" tiles: every cell of the inner region and its 4-neighbours is a boundary cell
+    // without an edge class (deep inside an obstacle).  Nothing there changes during a
+    // solve, so no pass touches them: once per solve their pressures are mirrored into the
+    // other buffer and their residual sum (a constant of the solve; the reference's norm
+    // counts obstacle cells too, src/simulation.rs:216-227) goes into one extra partial slot.
+    int n_frozen = 0;
+    int32_t *d_frozen = nullptr;     // tile ids
+    double *d_frozen_part = nullptr; // per-tile residual sums
+    size_t cap_frozen = 0;
+    uint64_t frozen_seq = 0;         // sb_sim::solve_seq the extra slot was filled for
 };
 
 #define SB_CUDA(call)                                                               \
@@ -197,6 +207,7 @@ struct sb_sim {
     size_t mid_cap = 0;
     int last_sor_path = 0, last_sor_ctas = 0;  // sb_last_sor_path
     bool mid_unavailable = false;             // a cooperative launch was refused on this device
+    uint64_t solve_seq = 0;                   // counts solve_sor calls (per-solve caches)
     uchar4 *d_img = nullptr;                  // RGBA8 frame of sb_render_rgba (lazy)
     // tensor maps for the red-black pass (built lazily per buffer)
     bool tmaps_ready = false;
@@ -234,6 +245,8 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h);
 sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h,
                                const RbFin *fin);
 void rb_plan_release(sb_sim *s);
+sb_status launch_frozen_mirror(sb_sim *s, int BX, int BY);   // frozen tiles: p[other] := p[cur]
+sb_status launch_frozen_fill(sb_sim *s, int part_stride, int slot);
 void preload_sor_rb_stream();
 // sor_small.cu: the whole red-black solve of a grid that fits one SM's shared memory
 bool sor_small_fits(const sb_sim *s);

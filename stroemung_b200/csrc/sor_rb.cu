@@ -656,7 +656,8 @@ sb_status launch_sor_rb_pass(sb_sim *s, int *nparts_out, int norm_only, const Rb
         n_items = s->plan.n_items;
         tile_list = s->plan.d_slow;
     }
-    const int nparts = n_tile + n_items;
+    const int n_frozen = (!norm_only && rb_stream_enabled()) ? s->plan.n_frozen : 0;
+    const int nparts = n_tile + n_items + (n_frozen ? 1 : 0);
     size_t need = (size_t)nparts * TMAX + 64;
     if (need > s->partial_cap) {  // stream-ordered: no device-wide synchronisation
         if (s->d_partial) SB_CUDA(cudaFreeAsync(s->d_partial, s->stream));
@@ -674,6 +675,20 @@ sb_status launch_sor_rb_pass(sb_sim *s, int *nparts_out, int norm_only, const Rb
     // tile row 0 is local row -h (even offset): the colour of the thread's first row follows
     // the parity of the slab's global row offset
     const int par = (int)(((g.gx0 % 2) + 2) % 2);
+    if (n_frozen && s->plan.frozen_seq != s->solve_seq) {
+        // first pass of a solve: mirror the frozen tiles' pressures into the other buffer and
+        // put their residual sum (constant for the whole solve) into the extra partial slot
+        if ((st = launch_frozen_mirror(s, BX, BY))) return st;
+        auto nk = s->slab ? (par ? sor_rb_kernel<1, true> : sor_rb_kernel<0, true>)
+                          : (par ? sor_rb_kernel<1, false> : sor_rb_kernel<0, false>);
+        nk<<<n_frozen, NTHR, SMEM_BYTES, s->stream>>>(s->tm_p[0], s->tm_p[1], s->tm_rhs, s->cflag, g,
+                                                      rb_pbuf_ptr(s), s->d_ctl,
+                                                      s->plan.d_frozen_part, tiles_y, n_frozen, h, k,
+                                                      1, peers, s->plan.d_frozen);
+        s->launches++;
+        if ((st = launch_frozen_fill(s, nparts, nparts - 1))) return st;
+        s->plan.frozen_seq = s->solve_seq;
+    }
     if (!norm_only) prof_mark(s);
     if (n_tile > 0) {
         auto kern = s->slab ? (par ? sor_rb_kernel<1, true> : sor_rb_kernel<0, true>)

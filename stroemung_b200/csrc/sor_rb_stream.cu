@@ -63,6 +63,7 @@ constexpr int IT_BC_LO = 4;    // the item's first row is a boundary row fed fro
 constexpr int IT_BC_HI = 8;    // the item's last row is a boundary row fed from the row before
 // tile classes of rb_class_kernel: 0 = tile kernel, 1 + item kind otherwise, plus
 constexpr int TC_BC_LO = 4, TC_BC_HI = 8;  // the tile owns grid row 0 / NX-1 as such a row
+constexpr int TC_FROZEN = 16;  // not streamable, but nothing in or next to the tile ever changes
 
 // Everything that indexes a ring is a compile-time constant inside the unrolled window:
 //   * the tick loop is unrolled over NW = 2T+4 ticks (the register window), U = tick mod NW;
@@ -642,8 +643,57 @@ __global__ void rb_class_kernel(const uint8_t *__restrict__ cflag, Geom g, int t
         }
     }
     ok = __syncthreads_and(ok);
+    // frozen: the inner region and one cell around it lie inside the grid (and this slab's
+    // rows) and hold nothing but boundary cells without an edge class
+    int frozen = 1;
+    {
+        const int64_t fc = (int64_t)tj * BY - 1 + threadIdx.x;   // columns tj BY - 1 .. + BY
+        const int64_t fc1 = min((int64_t)tj * BY + BY, g.NY) + 1;
+        if (fc < fc1) {
+            if (fc < 0 || fc >= g.NY) frozen = 0;
+            for (int64_t r = x0 - 1; frozen && r < x1 + 1; r++) {
+                const int64_t gx = g.gx0 + r;
+                if (gx < 0 || gx >= g.NX || r < 0 || r >= g.nxl) { frozen = 0; break; }
+                const uint8_t f = cflag[r * g.pitch + fc];
+                if (!cf_is_boundary(f) || cf_edge(f) != SB_EDGE_NONE) frozen = 0;
+            }
+        }
+    }
+    frozen = __syncthreads_and(frozen);
     if (threadIdx.x == 0)
-        cls[tile] = ok ? (uint8_t)(1 + kind + (bc_lo ? TC_BC_LO : 0) + (bc_hi ? TC_BC_HI : 0)) : 0;
+        cls[tile] = ok ? (uint8_t)(1 + kind + (bc_lo ? TC_BC_LO : 0) + (bc_hi ? TC_BC_HI : 0))
+                       : (frozen ? (uint8_t)TC_FROZEN : (uint8_t)0);
+}
+
+// p[other] := p[current] on the inner regions of the frozen tiles (once per solve)
+__global__ void frozen_mirror_kernel(const int32_t *__restrict__ tiles, Geom g, int tiles_y, int BX,
+                                     int BY, double *const *__restrict__ pbuf,
+                                     const SorCtl *__restrict__ ctl) {
+    const int tile = tiles[blockIdx.x];
+    const int ti = tile / tiles_y, tj = tile - ti * tiles_y;
+    const int64_t x0 = g.own0 + (int64_t)ti * BX, x1 = min(x0 + BX, g.own1);
+    const int64_t y0 = (int64_t)tj * BY, y1 = min(y0 + BY, g.NY);
+    const double *src = pbuf[ctl->src];
+    double *dst = pbuf[ctl->src ^ 1];
+    for (int64_t r = x0; r < x1; r++)
+        for (int64_t y = y0 + threadIdx.x; y < y1; y += blockDim.x)
+            dst[r * g.pitch + y] = src[r * g.pitch + y];
+}
+
+// the frozen tiles' residual sum (fixed order) -> the extra partial slot of every level
+__global__ void frozen_fill_kernel(const double *__restrict__ part, int n, double *__restrict__ partial,
+                                   int part_stride, int slot, int levels) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
+    acc = warp_sum_down(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += sh[k];
+        for (int l = 0; l < levels; l++) partial[(int64_t)l * part_stride + slot] = t;
+    }
 }
 
 }  // namespace
@@ -674,6 +724,8 @@ void rb_plan_release(sb_sim *s) {
     cudaFree(s->plan.d_items);
     cudaFree(s->plan.d_plain);
     cudaFree(s->plan.d_counter);
+    cudaFree(s->plan.d_frozen);
+    cudaFree(s->plan.d_frozen_part);
     s->plan = RbPlan();
 }
 
@@ -753,6 +805,24 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
             int t0 = ti;
             while (ti < tiles_x && (cls[(size_t)ti * tiles_y + tj] & 3) == k) ti++;
             runs.push_back({tj, t0, ti - t0, k - 1, k - 1 == IT_PLAIN ? 1.0 : wall_weight});
+        }
+    }
+    std::vector<int32_t> frozen;
+    {
+        const char *e = getenv("SB_RB_FROZEN");   // 0: frozen tiles stay on the tile kernel (A/B)
+        const bool use_frozen = !(e && atoi(e) == 0);
+        for (int t = 0; t < ntiles; t++) {
+            if (cls[(size_t)t] != TC_FROZEN) continue;
+            bool keep_frozen = use_frozen;
+            if (s->slab) {  // next to a slab edge the tile kernel also feeds the neighbour's halo
+                const int ti = t / tiles_y;
+                const int64_t x0 = g.own0 + (int64_t)ti * BX, x1 = std::min<int64_t>(x0 + BX, g.own1);
+                if ((s->link.lo_p[0] && x0 < g.own0 + s->link.H) ||
+                    (s->link.hi_p[0] && x1 > g.own1 - s->link.H))
+                    keep_frozen = false;
+            }
+            if (keep_frozen) frozen.push_back(t);
+            else cls[(size_t)t] = 0;
         }
     }
     for (int t = 0; t < ntiles; t++)
@@ -914,6 +984,20 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
         SB_CUDA(cudaMallocAsync(&pl.d_items, items.size() * sizeof(RbItem), s->stream));
         pl.cap_items = items.size();
     }
+    if (frozen.size() > pl.cap_frozen) {
+        if (pl.d_frozen) SB_CUDA(cudaFreeAsync(pl.d_frozen, s->stream));
+        if (pl.d_frozen_part) SB_CUDA(cudaFreeAsync(pl.d_frozen_part, s->stream));
+        pl.d_frozen = nullptr; pl.d_frozen_part = nullptr;
+        pl.cap_frozen = 0;
+        SB_CUDA(cudaMallocAsync(&pl.d_frozen, frozen.size() * sizeof(int32_t), s->stream));
+        SB_CUDA(cudaMallocAsync(&pl.d_frozen_part, frozen.size() * sizeof(double), s->stream));
+        pl.cap_frozen = frozen.size();
+    }
+    if (!frozen.empty())
+        SB_CUDA(cudaMemcpyAsync(pl.d_frozen, frozen.data(), frozen.size() * sizeof(int32_t),
+                                cudaMemcpyHostToDevice, s->stream));
+    pl.n_frozen = (int)frozen.size();
+    pl.frozen_seq = 0;
     if (!slow.empty())
         SB_CUDA(cudaMemcpyAsync(pl.d_slow, slow.data(), slow.size() * sizeof(int32_t),
                                 cudaMemcpyHostToDevice, s->stream));
@@ -929,10 +1013,10 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
             nbc += (it.pad & (IT_BC_LO | IT_BC_HI)) != 0;
             longest = std::max(longest, it.x1 - it.x0);
         }
-        fprintf(stderr, "[sb plan] T=%d tiles %dx%d slow %zu items %zu (plain %d, wall %d+%d, with "
-                "boundary rows %d) longest %d rows, seg %d, resident CTAs %lld\n", T, tiles_x,
-                tiles_y, slow.size(), items.size(), nk[0], nk[1], nk[2], nbc, longest, best_seg,
-                (long long)resident);
+        fprintf(stderr, "[sb plan] T=%d tiles %dx%d slow %zu frozen %zu items %zu (plain %d, wall %d+%d, "
+                "with boundary rows %d) longest %d rows, seg %d, resident CTAs %lld\n", T, tiles_x,
+                tiles_y, slow.size(), frozen.size(), items.size(), nk[0], nk[1], nk[2], nbc, longest,
+                best_seg, (long long)resident);
     }
     pl.n_slow = (int)slow.size();
     pl.n_items = (int)items.size();
@@ -981,10 +1065,29 @@ sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h,
     return SB_OK;
 }
 
+sb_status launch_frozen_mirror(sb_sim *s, int BX, int BY) {
+    const int tiles_y = (int)((s->g.NY + BY - 1) / BY);
+    frozen_mirror_kernel<<<s->plan.n_frozen, 128, 0, s->stream>>>(s->plan.d_frozen, s->g, tiles_y, BX,
+                                                                  BY, rb_pbuf_ptr(s), s->d_ctl);
+    s->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+sb_status launch_frozen_fill(sb_sim *s, int part_stride, int slot) {
+    frozen_fill_kernel<<<1, 1024, 0, s->stream>>>(s->plan.d_frozen_part, s->plan.n_frozen, s->d_partial,
+                                                  part_stride, slot, RB_TMAX);
+    s->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
 void preload_sor_rb_stream() {
     cudaFuncAttributes a;
     for (int tb = 1; tb <= RB_TMAX; tb++) cudaFuncGetAttributes(&a, stream_kernel(tb));
     cudaFuncGetAttributes(&a, rb_class_kernel);
+    cudaFuncGetAttributes(&a, frozen_mirror_kernel);
+    cudaFuncGetAttributes(&a, frozen_fill_kernel);
     cudaGetLastError();
 }
 

@@ -660,3 +660,46 @@ def test_mid_kernel_early_exit():
     assert_bits_equal(sim.grid.pressure, o.p, "p")
     assert_bits_equal(sim.grid.u, o.u, "u")
     assert list(sim.grid.pressure_range) == list(o.state().pressure_range)
+
+
+# ---- frozen tiles: deep inside an obstacle no pass touches anything ------------------------
+@pytest.mark.parametrize("T", [1, 2, 3, 4])
+def test_frozen_tiles_inside_a_block_match_oracle(T, monkeypatch):
+    """A large NoSlip block (the backward-facing step of BASELINE config 4 in small): the tiles
+    deep inside it are left out of every pass -- their pressures are mirrored into the other
+    buffer once per solve and their residual sum (the reference's norm counts obstacle
+    cells, simulation.rs:216-227) is added as a constant.  Fields bit-exact vs the oracle,
+    norms within the summation-order allowance, and identical to the run that keeps those
+    tiles on the tile kernel."""
+    if SOR_PATH != "pass-kernels":
+        pytest.skip("about the pass kernels")
+    nx, ny = 300, 520
+    kind, bu, bv = po.preset("simple_inflow", nx, ny)
+    kind = kind.copy()
+    kind[40:260, 130:500] = 1          # NoSlip block, away from the ring
+    p, u, v = random_fields(nx, ny, 71)   # random p inside the block too: residuals there != 0
+    unf = unfinalized(nx, ny, kind, bu, bv, p=p, u=u, v=v)
+    o = oracle_from(unf, sor_mode=po.SOR_RED_BLACK)
+    got = {}
+    for frozen in ("1", "0"):
+        monkeypatch.setenv("SB_RB_FROZEN", frozen)
+        sim = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK, temporal_block=T)
+        norms = sim.sor_sweeps(7)
+        plan = sim.rb_plan
+        ticks = [sim.run_simulation_tick() for _ in range(2)]
+        got[frozen] = (norms, plan, ticks, sim.grid.pressure, sim.grid.u, sim.grid.v)
+        sim.close()
+    assert got["1"][1][0] < got["0"][1][0], (got["1"][1], got["0"][1])   # fewer tile-kernel tiles
+    norms = got["1"][0]
+    for k in range(7):
+        o.sor_sweep()
+        assert close(norms[k], o.calculate_norm_squared()), (k, norms[k])
+        assert close(norms[k], got["0"][0][k])
+    for t in range(2):
+        oit, onrm = o.run_simulation_tick()
+        it, nrm = got["1"][2][t]
+        assert it == oit and close(nrm, onrm), (t, it, oit, nrm, onrm)
+    for i, name in ((3, "p"), (4, "u"), (5, "v")):
+        assert_bits_equal(got["1"][i], got["0"][i], name + " frozen vs tile kernel")
+    assert_bits_equal(got["1"][3], o.p, "p")
+    assert_bits_equal(got["1"][4], o.u, "u")
