@@ -358,6 +358,7 @@ def run_ours(args):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "dram_gbs": traffic / (avg_ms * 1e-3) / 1e9 if traffic else None,
+                "dram_frac": traffic / (avg_ms * 1e-3) / 1e9 / peak if traffic else None,
                 "peak_source": peak_src, "launches_timed": len(work),
                 "avg_launch_ms": avg_ms, "sweeps_per_launch": sweeps_per_launch,
                 "launch_ms_min_median_max": [min(work), statistics.median(work), max(work)],
