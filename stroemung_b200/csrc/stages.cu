@@ -200,7 +200,14 @@ __device__ __forceinline__ void fgr_cell(const Stencil9 &su, const Stencil9 &sv,
     if (need_g) gv = calculate_g(su, sv, dv.k, delt, gamma);
 }
 
-__global__ void __launch_bounds__(32 * FGR_WARPS, 3)
+// Three CTAs per SM: 80 registers and 36 bytes of spills -- the row load_row() prefetches is
+// spilled right after the load, and the STL waiting for that load shows up with 23 % of the
+// kernel's stall samples (profiles/r1_fg_rhs_8192_stalls.txt).  Two CTAs per SM (121 registers,
+// no spills, -DFGR_MINB=2) were measured and are not faster: non-SOR part of a tick 2.42 vs 2.32 ms.
+#ifndef FGR_MINB
+#define FGR_MINB 3
+#endif
+__global__ void __launch_bounds__(32 * FGR_WARPS, FGR_MINB)
 fg_rhs_kernel(Geom g, const double *__restrict__ u, const double *__restrict__ v,
               const uint8_t *__restrict__ cflag, double *__restrict__ f, double *__restrict__ gq,
               double *__restrict__ rhs, int64_t fg_row0, int64_t row1, int64_t rhs_row0,
