@@ -125,3 +125,30 @@ def test_obstacle_preset_default_config_three_ticks():
         assert_bits_equal(getattr(o, name), arr(getattr(s, name)), name)
     st = o.state()
     assert list(st.pressure_range) == s.pressure_range and list(st.speed_range) == s.speed_range
+
+
+@pytest.mark.parametrize("eps", [1e-3, 1e-6])
+def test_oracle_red_black_agrees_with_reference_order_when_converged(eps):
+    """Performance-mode parity bar at the oracle level (BASELINE north star): on
+    converged ticks the red-black ordering gives the reference-order fields within the SOR
+    tolerance -- u, v and the mean-removed p, fluid cells only.  A closed lid-driven cavity has a
+    solvable pressure problem every tick (the channel presets hit the sweep cap instead)."""
+    from stroemung_b200 import presets
+    from tests.util import oracle_from, unfinalized
+    shape = (34, 34)
+    g = presets.cavity(shape, lid_u=1.0)
+    unf = unfinalized(shape[0], shape[1], g["kind"], g["bu"], g["bv"], delx=1 / 32, dely=1 / 32,
+                      delt=2e-3, reynolds=100.0, sor_absolute_epsilon=eps, max_iterations=5000)
+    rb = oracle_from(unf, sor_mode=po.SOR_RED_BLACK)
+    lex = oracle_from(unf, sor_mode=po.SOR_REFERENCE_ORDER)
+    for t in range(60):
+        it_rb, n_rb = rb.run_simulation_tick()
+        it_lex, n_lex = lex.run_simulation_tick()
+        assert it_rb < 5000 and it_lex < 5000, (t, it_rb, it_lex, n_rb, n_lex)
+    fluid = g["kind"] == 0
+    du = np.abs(rb.u - lex.u)[fluid].max()
+    dv = np.abs(rb.v - lex.v)[fluid].max()
+    dp = np.abs((rb.p - rb.p[fluid].mean()) - (lex.p - lex.p[fluid].mean()))[fluid].max()
+    assert np.abs(lex.u)[fluid].max() > 0.05   # the lid has set the fluid in motion
+    tol = 3.0 * eps
+    assert du <= tol and dv <= tol and dp <= tol, (du, dv, dp)
