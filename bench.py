@@ -56,8 +56,17 @@ def ncu_traffic(key):
 
 def workload(name, n_gpus, size=None):
     """-> dict(preset, preset_args, size, scalar parameters) of one BASELINE config."""
-    if name == "c5":   # SOR-dominated scaling sweep: channel, 100 fixed sweeps per tick
-        nx, ny = size or (8192 * n_gpus, 8192)
+    wl = _workload(name, n_gpus, size)
+    wl["key"] = name
+    # only c5 grows with N ((8192 N) x 8192); every other workload is a fixed grid cut into N slabs
+    wl["scaling"] = "weak" if (name == "c5" and size is None) else "strong"
+    return wl
+
+
+def _workload(name, n_gpus, size=None):
+    if name in ("c5", "c5s"):   # SOR-dominated scaling sweep: channel, 100 fixed sweeps per tick
+        # c5: weak -- (8192 N) x 8192 on N GPUs; c5s: strong -- 32768^2 (or --size) whatever N
+        nx, ny = size or ((8192 * n_gpus, 8192) if name == "c5" else (32768, 32768))
         return dict(name="c5-sor-dominated-channel", preset="simple_inflow", preset_args=(),
                     size=(nx, ny), cell_size=(10.0 / ny, 10.0 / ny), delt=2e-4, gamma=0.9,
                     reynolds=100.0, eps=0.0, max_iterations=100, omega=1.7)
@@ -171,7 +180,7 @@ def cpu_sample(wl, ticks, sample=(2048, 2048)):
     from oracle import pyoracle as po
     from stroemung_b200 import presets
     nx, ny = min(sample[0], wl["size"][0]), min(sample[1], wl["size"][1])
-    sub = workload(wl["name"].split("-")[0], 1, (nx, ny))  # same shape rules, smaller grid
+    sub = workload(wl["key"], 1, (nx, ny))  # same shape rules, smaller grid
     a = sub["preset_args"]
     if sub["preset"] == "channel_circle":
         g = presets.channel_circle((nx, ny), int(a[0]), int(a[1]), float(a[2]))
@@ -186,14 +195,27 @@ def cpu_sample(wl, ticks, sample=(2048, 2048)):
                      gamma=wl["gamma"], reynolds=wl["reynolds"],
                      sor_absolute_epsilon=wl["eps"], max_iterations=wl["max_iterations"],
                      omega=wl["omega"], kind=kind, bu=bu, bv=bv)
-    t0 = time.perf_counter()
-    sweeps = 0
-    for _ in range(ticks):
-        it, _ = o.run_simulation_tick()
-        sweeps += it
-    dt = time.perf_counter() - t0
+    # one thread pinned to one core (the reference is single-threaded)
+    pinned = None
+    try:
+        old = os.sched_getaffinity(0)
+        core = max(old)
+        os.sched_setaffinity(0, {core})
+        pinned = core
+    except (AttributeError, OSError):
+        old = None
+    try:
+        t0 = time.perf_counter()
+        sweeps = 0
+        for _ in range(ticks):
+            it, _ = o.run_simulation_tick()
+            sweeps += it
+        dt = time.perf_counter() - t0
+    finally:
+        if old is not None:
+            os.sched_setaffinity(0, old)
     return {"value": nx * ny * ticks / dt / 1e6, "seconds": dt, "grid": [nx, ny],
-            "ticks": ticks, "sweeps": sweeps}
+            "ticks": ticks, "sweeps": sweeps, "pinned_core": pinned}
 
 
 def run_reference(args):
@@ -201,17 +223,21 @@ def run_reference(args):
     if rank != 0:
         return 0
     wl = workload(args.workload, args.gpus, args.size)
+    # the real grid whenever it is <= 2048^2 cells, else a 2048^2 sample of the same preset
     sample = (2048, 2048) if wl["size"][0] * wl["size"][1] > 2048 * 2048 else wl["size"]
     cpu_sample(wl, max(args.warmup, 0) and 1, sample=(256, 256))  # warm the code / caches
+    # bounded: a 2048^2 tick of 100 sweeps takes ~6 s on one core, 20 steps ~2 minutes
     r = cpu_sample(wl, args.steps, sample)
-    sample_txt = (f"{r['grid'][0]}x{r['grid'][1]} grid of the same preset and parameters, "
-                  f"{r['ticks']} ticks, {r['sweeps']} lexicographic SOR sweeps, C oracle "
-                  f"(port of the Rust reference), 1 thread")
+    sample_txt = (f"{r['grid'][0]}x{r['grid'][1]} grid of the same preset and parameters"
+                  f"{' (a sample: per-cell rate)' if list(r['grid']) != list(wl['size']) else ''}, "
+                  f"{r['ticks']} ticks, {r['sweeps']} lexicographic SOR sweeps, {r['seconds']:.1f} s, "
+                  f"C oracle (port of the Rust reference), 1 thread pinned to core "
+                  f"{r['pinned_core']}")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "ms_per_step": 1e3 * r["seconds"] / max(r["ticks"], 1), "higher_is_better": True,
+        "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["name"], "grid": list(wl["size"]), "sample": sample_txt,
                    "sweeps_per_tick": r["sweeps"] / max(r["ticks"], 1)},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": 1, "kind": "port",
@@ -221,6 +247,82 @@ def run_reference(args):
     }
     print(json.dumps(line))
     return 0
+
+
+# ---- verification on the bench grid ----------------------------------------------------------
+def host_preset(wl):
+    from stroemung_b200 import presets
+    nx, ny = wl["size"]
+    a = wl["preset_args"]
+    if wl["preset"] == "channel_circle":
+        return presets.channel_circle((nx, ny), int(a[0]), int(a[1]), float(a[2]))
+    if wl["preset"] == "backward_step":
+        return presets.backward_step((nx, ny), int(a[0]), int(a[1]))
+    if wl["preset"] == "cavity":
+        return presets.cavity((nx, ny), float(a[0]))
+    return getattr(presets, wl["preset"])((nx, ny))
+
+
+def verify_on_bench_grid(wl, mode, tblock, device, sweeps=8, tick_sweeps=4):
+    """The kernels, plan and grid of the timed region against the CPU oracle (the checker,
+    never the thing measured): from a seeded random state (p, u, v ~ U(-0.5, 0.5), splitmix-
+    seeded numpy generator) `sweeps` SOR sweeps and one full tick capped at `tick_sweeps`
+    sweeps, on the bench grid with the bench's mask, parameters and temporal block.
+    p after the sweeps and p, u, v after the tick must be bit-identical (red-black: to the
+    oracle's red-black restatement; lex: to the reference order), norms within 1e-12."""
+    from oracle import pyoracle as po
+    from stroemung_b200.simulation import SOR_RED_BLACK, SOR_REFERENCE_ORDER, Simulation
+    t0 = time.perf_counter()
+    nx, ny = wl["size"]
+    rng = np.random.default_rng(0x5EED5EED)
+    p, u, v = (rng.uniform(-0.5, 0.5, (nx, ny)) for _ in range(3))
+    g = host_preset(wl)
+    prm = dict(delx=wl["cell_size"][0], dely=wl["cell_size"][1], delt=wl["delt"],
+               gamma=wl["gamma"], reynolds=wl["reynolds"], sor_absolute_epsilon=wl["eps"],
+               max_iterations=tick_sweeps, omega=wl["omega"])
+    rb = mode == "rb"
+    o = po.OracleSim(nx, ny, kind=g["kind"], bu=g["bu"], bv=g["bv"], p=p, u=u, v=v,
+                     sor_mode=po.SOR_RED_BLACK if rb else po.SOR_REFERENCE_ORDER, **prm)
+    unf = {"size": (nx, ny), "cell_size": wl["cell_size"], "delt": wl["delt"],
+           "gamma": wl["gamma"], "reynolds": wl["reynolds"], "sor_absolute_epsilon": wl["eps"],
+           "max_iterations": tick_sweeps, "omega": wl["omega"],
+           "grid": {"p": p, "u": u, "v": v, "kind": g["kind"], "bu": g["bu"], "bv": g["bv"]}}
+    sim = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK if rb else SOR_REFERENCE_ORDER,
+                              temporal_block=tblock, device=device)
+    del p, u, v
+
+    def same(a, b):
+        return bool(np.array_equal(np.ascontiguousarray(a).view(np.uint64),
+                                   np.ascontiguousarray(b).view(np.uint64)))
+
+    def close(a, b):
+        return a == b or abs(a - b) <= 1e-12 * max(abs(a), abs(b))
+
+    bad = []
+    norms = sim.sor_sweeps(sweeps)
+    for k in range(sweeps):
+        o.sor_sweep()
+        if not close(norms[k], o.calculate_norm_squared()):
+            bad.append(f"norm of sweep {k}")
+    if not same(sim.grid.pressure, o.p):
+        bad.append("p after sweeps")
+    it, nrm = sim.run_simulation_tick()
+    oit, onrm = o.run_simulation_tick()
+    if it != oit or not close(nrm, onrm):
+        bad.append("tick (iterations, norm)")
+    for name, a, b in (("p", sim.grid.pressure, o.p), ("u", sim.grid.u, o.u),
+                       ("v", sim.grid.v, o.v)):
+        if not same(a, b):
+            bad.append(f"{name} after tick")
+    plan = list(sim.rb_plan) if rb else None
+    path = sim.sor_path[0] if rb else None
+    sim.close()
+    return {"result": "bit-exact" if not bad else "MISMATCH: " + ", ".join(bad),
+            "grid": [nx, ny], "sweeps": sweeps, "tick_sweeps": it,
+            "fields": "p after sweeps; p, u, v after one tick (random initial p, u, v)",
+            "norm_rtol": 1e-12, "against": "oracle/stroemung_oracle.c "
+            + ("red-black restatement" if rb else "reference order"),
+            "rb_plan": plan, "sor_path": path, "seconds": time.perf_counter() - t0}
 
 
 # ---- our arm -----------------------------------------------------------------------------
@@ -377,11 +479,22 @@ def run_ours(args):
     cpu = None
     if n_gpus == 1 and not args.no_cpu:
         sample = (2048, 2048) if cells > 2048 * 2048 else wl["size"]
-        r = cpu_sample(wl, 2 if cells > 2048 * 2048 else min(args.steps, 20), sample)
+        cells_s = min(sample[0], nx) * min(sample[1], ny)
+        r = cpu_sample(wl, 5 if cells_s * wl["max_iterations"] >= 2e7 else min(args.steps, 20),
+                       sample)
         cpu = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{r['grid'][0]}x{r['grid'][1]} grid of the same preset/parameters, "
                          f"{r['ticks']} ticks, {r['sweeps']} lexicographic sweeps, "
-                         f"{r['seconds']:.1f} s, C oracle (port of the Rust reference), 1 thread"}
+                         f"{r['seconds']:.1f} s, C oracle (port of the Rust reference), 1 thread "
+                         f"pinned to core {r['pinned_core']}"}
+    # -- verification of the timed kernels on the bench grid (N = 1; slabs: tests/) ----------
+    verify = None
+    if n_gpus == 1 and not args.no_verify:
+        if cells <= 8192 * 8192:
+            verify = verify_on_bench_grid(wl, args.mode, args.tblock, local_rank)
+        else:
+            verify = {"result": "skipped", "why": "grid larger than 8192^2: the CPU oracle would "
+                      "need minutes; the same plan shapes are verified in tests/test_gpu_scale.py"}
 
     ws_mb = local_cells * 57 / 1e6   # 7 f64 arrays + flags
     kfix = TICK_FIXED_BYTES_PER_CELL
@@ -389,8 +502,11 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["name"], "grid": [nx, ny], "sor_mode": args.mode,
+                   "initial_state": "fields at rest (p = u = v = 0; the inflow starts the flow); "
+                                    "f64 arithmetic time does not depend on the values, and "
+                                    "`verify` below runs the same kernels from a random state",
                    "temporal_block": T, "sweeps_per_tick": k_avg,
                    "slabs": f"{n_gpus} row slab(s) along x",
                    "rb_plan": {"tile_kernel_tiles": rb_plan[0], "stream_items": rb_plan[1]}
@@ -412,7 +528,7 @@ def run_ours(args):
                           (kfix + SOR_BYTES_PER_CELL_SWEEP * k_avg) / 1e6,
                           "frac": value / (n_gpus * peak * 1e9 /
                                            (kfix + SOR_BYTES_PER_CELL_SWEEP * k_avg) / 1e6)},
-        "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+        "roofline": roof, "cpu_baseline": cpu, "verify": verify, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * nbytes * n_gpus,
                 "d2h_bytes_per_step": 3 * nbytes * n_gpus, "steps": e2e_steps},
         "gpu_launches": launches,
@@ -434,6 +550,7 @@ def main():
     ap.add_argument("--mode", default="rb", choices=["rb", "lex"])
     ap.add_argument("--tblock", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
     if args.size is not None:
         args.size = tuple(args.size)

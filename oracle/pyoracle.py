@@ -95,6 +95,8 @@ def lib():
     L.so_get_state.restype = None
     L.so_set_params.argtypes = [vp, C.POINTER(Params)]
     L.so_set_params.restype = None
+    L.so_clear_initial_norm.argtypes = [vp]
+    L.so_clear_initial_norm.restype = None
     L.so_boundary_list.argtypes = [vp, u64p, u8p, C.c_uint64]
     L.so_boundary_list.restype = C.c_uint64
     d = C.c_double
@@ -262,6 +264,10 @@ class OracleSim:
         for k, val in kw.items():
             setattr(self.prm, k, val)
         lib().so_set_params(self._h, C.byref(self.prm))
+
+    def clear_initial_norm(self):
+        """sim.initial_norm_squared = None (pub field, src/simulation.rs:62)"""
+        lib().so_clear_initial_norm(self._h)
 
     def rebuild_boundary_list(self):
         err = (C.c_uint64 * 2)()

@@ -748,6 +748,13 @@ void so_set_params(so_sim *s, const so_params *prm) {
     s->prm.ny = ny;
 }
 
+/* sim.initial_norm_squared = None (the field is pub, src/simulation.rs:62): the next
+ * solve_sor latches the norm after its first sweep (src/simulation.rs:229-237, 276) */
+void so_clear_initial_norm(so_sim *s) {
+    s->has_initial_norm = 0;
+    s->initial_norm_squared = 0.0;
+}
+
 uint64_t so_boundary_list(const so_sim *s, uint64_t *idx, uint8_t *edge, uint64_t cap) {
     uint64_t n = s->n_boundary < cap ? s->n_boundary : cap;
     for (uint64_t k = 0; k < n; k++) {

@@ -133,6 +133,7 @@ typedef struct {
 } so_state;
 void so_get_state(const so_sim *s, so_state *st);
 void so_set_params(so_sim *s, const so_params *prm); /* scalar fields only */
+void so_clear_initial_norm(so_sim *s);  /* initial_norm_squared = None */
 
 /* boundary list read-back: idx = x*ny+y, edge = SO_EDGE_*; returns count */
 uint64_t so_boundary_list(const so_sim *s, uint64_t *idx, uint8_t *edge, uint64_t cap);

@@ -1,6 +1,6 @@
 #!/bin/bash
 # usage: scripts/kernel_times.sh [bench args...]   -- per-kernel average durations of one tick (ncu, cold)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_small.csv python bench.py --steps 1 --warmup 1 --no-cpu "$@" > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_small.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-verify "$@" > /dev/null 2>&1
 python - <<EOF
 import csv,collections
 rows=[r for r in csv.reader(open("gpurun_out/launches_small.csv")) if len(r)>10 and r[0].isdigit()]

@@ -33,6 +33,28 @@ void prof_mark(sb_sim *s) {
     cudaEventRecord(s->prof_events[s->prof_used++], s->stream);
 }
 
+// the library's only look at the environment: test hooks and trace switches (DebugKnobs)
+static DebugKnobs read_debug_knobs() {
+    DebugKnobs k;
+    auto geti = [](const char *name, int dflt) {
+        const char *e = getenv(name);
+        return e ? atoi(e) : dflt;
+    };
+    k.sor_small = geti("SB_SOR_SMALL", 1) != 0;
+    k.sor_mid = geti("SB_SOR_MID", 1) != 0;
+    k.sor_mid_ctas = geti("SB_SOR_MID_CTAS", 0);
+    k.sor_mid_variant = geti("SB_SOR_MID_VARIANT", 0);
+    k.rb_stream = geti("SB_RB_STREAM", 1) != 0;
+    k.rb_stream_kinds = geti("SB_RB_STREAM_KINDS", 3);
+    k.rb_frozen = geti("SB_RB_FROZEN", 1) != 0;
+    if (const char *e = getenv("SB_WALL_WEIGHT")) k.wall_weight = atof(e);
+    k.trace_plan = getenv("SB_DEBUG_PLAN") != nullptr;
+    k.trace_stream = getenv("SB_STREAM_TRACE") != nullptr;
+    k.trace_mid = getenv("SB_MID_TRACE") != nullptr;
+    k.trace_fin = getenv("SB_FIN_TRACE") != nullptr;
+    return k;
+}
+
 static bool is_rb(const sb_sim *s) { return s->prm.sor_mode == SB_SOR_RED_BLACK; }
 
 static sb_status validate(const sb_params *p) {
@@ -94,6 +116,7 @@ static sb_status allocate(const sb_params *params, sb_sim **out) {
     sb_sim *s = new (std::nothrow) sb_sim();
     if (!s) return SB_INVALID_ARGUMENT;
     s->prm = *params;
+    s->dbg = read_debug_knobs();
     if (s->prm.temporal_block == 0) s->prm.temporal_block = 4;
     if (params->device >= 0) s->device = params->device;
     else cudaGetDevice(&s->device);
@@ -132,16 +155,6 @@ static sb_status allocate(const sb_params *params, sb_sim **out) {
     g.own0 = s->halo;
     g.own1 = s->halo + (xe - xb);
     g.pitch = round_up(g.NY, 16);
-    {
-        // Experiment knob (default off): SB_PITCH_PAD=n adds n elements to a row pitch that is a
-        // multiple of 2 KB.  The wall strips of a channel run 1.5-2.5x slower per row than a
-        // plain strip and all their warps advance in lockstep (per-item trace) -- which looks
-        // like all rows of a strip queueing on a few HBM channels -- but padding the pitch by
-        // 128 B .. 8 KB did not change that (profiles/r1_wall_strip_experiments.txt).
-        const char *e = getenv("SB_PITCH_PAD");
-        const int pad = e ? atoi(e) : 0;
-        if (pad > 0 && (g.pitch * (int64_t)sizeof(double)) % 2048 == 0) g.pitch += round_up(pad, 16);
-    }
     s->field_bytes = (size_t)g.nxl * g.pitch * sizeof(double);
     s->flag_bytes = (size_t)g.nxl * g.pitch;
 #define SB_TRY(call)                                                            \
@@ -282,6 +295,29 @@ static sb_status solve(sb_sim *s, uint32_t max_it, int test_exit, uint32_t *iter
         }
         d_hist = s->d_hist;
     }
+    if (test_exit && !s->has_initial_norm && max_it > 0 && s->g.NX >= 3 && s->g.NY >= 3) {
+        // initial_norm_squared == None (only reachable through sb_set_params: try_from always
+        // latches it): get_initial_norm_squared (src/simulation.rs:229-237) then computes and
+        // caches the norm AFTER the first sweep (:276), so iteration 0 can only leave through
+        // the eps test.  One sweep without the exit rule, latch, test, then the rest.
+        uint32_t it1 = 0;
+        double n1 = 0.0;
+        if ((st = solve(s, 1, 0, &it1, &n1, nullptr))) return st;
+        s->has_initial_norm = 1;
+        s->initial_norm_squared = n1;
+        const double e2 = s->prm.sor_absolute_epsilon * s->prm.sor_absolute_epsilon;
+        if (n1 < e2 || max_it == 1) {
+            *iters = 1;
+            *norm = n1;
+            const int capped = !(n1 < e2);
+            if (cap_hit_out) *cap_hit_out = capped;
+            else if (capped && (st = launch_pressure_range(s))) return st;
+            return SB_OK;
+        }
+        st = solve(s, max_it - 1, 1, iters, norm, nullptr, cap_hit_out);
+        *iters += 1;
+        return st;
+    }
     s->solve_seq++;
     SB_CUDA(cudaEventRecord(s->ev_sor0, s->stream));
     if (max_it == 0 || s->g.NX < 3 || s->g.NY < 3) {
@@ -339,7 +375,7 @@ static sb_status solve(sb_sim *s, uint32_t max_it, int test_exit, uint32_t *iter
             set_error("SOR grid barrier timed out (sor_mid.cu)");
             return SB_CUDA_ERROR;
         }
-        if (mid && s->last_sor_path == 3 && getenv("SB_MID_TRACE")) {
+        if (mid && s->last_sor_path == 3 && s->dbg.trace_mid) {
             const double n = std::max(1u, h->iters_done);
             fprintf(stderr, "sor_mid_reg: %u sweeps; cycles per sweep on CTA 0: BC %.0f, red %.0f, "
                             "black %.0f, red residual + publish %.0f, grid barrier %.0f, halo + "
@@ -400,7 +436,12 @@ static sb_status solve(sb_sim *s, uint32_t max_it, int test_exit, uint32_t *iter
 
 static sb_status tick(sb_sim *s, uint32_t *iters, double *norm) {
     sb_status st;
-    if (s->prm.tau > 0.0) adapt_delt(s);
+    if (s->prm.tau > 0.0) {
+        // the maxima cached by the last velocity update are stale after an upload of u / v or
+        // a re-classification: take them from the fields as they are now
+        if (!s->uvmax_valid && (st = launch_speed_range(s))) return st;
+        adapt_delt(s);
+    }
     if ((st = launch_velocity_bc(s))) return st;
     if ((st = launch_fg_rhs(s, 3))) return st;
     int prange_due = 0;
@@ -512,7 +553,7 @@ sb_status sb_create_preset(const sb_params *params, int32_t preset, const double
 }
 
 void sb_destroy(sb_sim *sim) {
-    if (sim && sim->slab && getenv("SB_FIN_TRACE")) {
+    if (sim && sim->slab && sim->dbg.trace_fin) {
         cudaSetDevice(sim->device);
         cudaStreamSynchronize(sim->stream);
         sb::dump_finalize_trace(sim->link.rank);
@@ -703,6 +744,7 @@ sb_status sb_upload(sb_sim *sim, sb_field field, const void *src) {
     }
     double *dst = field_ptr(sim, field);
     if (!dst) return SB_INVALID_ARGUMENT;
+    if (field == SB_FIELD_U || field == SB_FIELD_V) sim->uvmax_valid = false;
     if ((st = copy_rows_h2d(sim, dst, src, 8))) return st;
     SB_CUDA(cudaStreamSynchronize(sim->stream));
     return SB_OK;
@@ -790,8 +832,10 @@ sb_status sb_boundary_list(sb_sim *sim, uint64_t *index, uint8_t *edge, uint64_t
     if (m == 0) return SB_OK;
     std::vector<int64_t> lin(m);
     std::vector<uint8_t> ke(m);
-    SB_CUDA(cudaMemcpy(lin.data(), sim->bl.lin, m * sizeof(int64_t), cudaMemcpyDeviceToHost));
-    SB_CUDA(cudaMemcpy(ke.data(), sim->bl.ke, m, cudaMemcpyDeviceToHost));
+    SB_CUDA(cudaMemcpyAsync(lin.data(), sim->bl.lin, m * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                            sim->stream));
+    SB_CUDA(cudaMemcpyAsync(ke.data(), sim->bl.ke, m, cudaMemcpyDeviceToHost, sim->stream));
+    SB_CUDA(cudaStreamSynchronize(sim->stream));
     for (uint64_t k = 0; k < m; k++) {
         int64_t lx = lin[k] / sim->g.pitch, y = lin[k] - lx * sim->g.pitch;
         if (index) index[k] = (uint64_t)((sim->g.gx0 + lx) * sim->g.NY + y);

@@ -248,6 +248,9 @@ sb_status alloc_list(cudaStream_t st, BList &b, uint64_t n) {
 sb_status classify(sb_sim *s) {
     const Geom &g = s->g;
     s->flag_epoch++;
+    // u_v_restore is reset before the scan, so also when it fails (src/grid/mod.rs:205)
+    s->restore_valid = false;
+    s->uvmax_valid = false;   // the fluid set may change
     int64_t total = g.nxl * g.NY;
     unsigned long long init[2] = {~0ull, 0ull};
     SB_CUDA(cudaMemcpyAsync(s->d_err, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
@@ -314,12 +317,20 @@ sb_status classify(sb_sim *s) {
     s->launches++;
     SB_CUDA(cudaGetLastError());
     s->fluid_cells = (double)res[1];  // owned fluid cells; slab mode sums over ranks later
-    return apply_velocity_table(s);
+    sb_status st3 = apply_velocity_table(s);
+    if (st3) return st3;
+    // the list is complete when classify() returns (sb_boundary_list may read it right away)
+    SB_CUDA(cudaStreamSynchronize(s->stream));
+    return SB_OK;
 }
 
 sb_status apply_velocity_table(sb_sim *s) {
     size_t n = s->velocities.size();
-    if (n == 0 || s->bl.n == 0) return SB_OK;
+    if (s->bl.n == 0) return SB_OK;
+    // the table REPLACES the velocities: cells it no longer names go back to (0, 0)
+    SB_CUDA(cudaMemsetAsync(s->bl.bu, 0, s->bl.n * sizeof(double), s->stream));
+    SB_CUDA(cudaMemsetAsync(s->bl.bv, 0, s->bl.n * sizeof(double), s->stream));
+    if (n == 0) return SB_OK;
     sb_boundary_velocity *d_tab = nullptr;
     SB_CUDA(cudaMallocAsync(&d_tab, n * sizeof(sb_boundary_velocity), s->stream));
     SB_CUDA(cudaMemcpyAsync(d_tab, s->velocities.data(), n * sizeof(sb_boundary_velocity),

@@ -125,6 +125,25 @@ struct RbPlan {
     uint64_t frozen_seq = 0;         // sb_sim::solve_seq the extra slot was filled for
 };
 
+// Test hooks and diagnostics, read from the environment ONCE per handle (capi.cu:
+// read_debug_knobs, the only getenv of the library) -- none of them changes results, they
+// select which of several bit-identical kernels runs (so that the parity tests can drive
+// every path on every shape) or print traces.
+struct DebugKnobs {
+    bool sor_small = true;     // SB_SOR_SMALL=0: small grids off the one-SM solve
+    bool sor_mid = true;       // SB_SOR_MID=0: mid-size grids off the grid-resident solve
+    int sor_mid_ctas = 0;      // SB_SOR_MID_CTAS=n: force a decomposition (0 = natural)
+    int sor_mid_variant = 0;   // SB_SOR_MID_VARIANT=1|2: generic / register-window kernel
+    bool rb_stream = true;     // SB_RB_STREAM=0: every tile on the tile kernel
+    int rb_stream_kinds = 3;   // SB_RB_STREAM_KINDS: bit 0 wall strips, bit 1 boundary rows
+    bool rb_frozen = true;     // SB_RB_FROZEN=0: frozen tiles stay on the tile kernel
+    double wall_weight = 0.0;  // SB_WALL_WEIGHT: plan weight of a wall row (0 = default)
+    bool trace_plan = false;   // SB_DEBUG_PLAN
+    bool trace_stream = false; // SB_STREAM_TRACE
+    bool trace_mid = false;    // SB_MID_TRACE
+    bool trace_fin = false;    // SB_FIN_TRACE
+};
+
 #define SB_CUDA(call)                                                               \
     do {                                                                            \
         cudaError_t _e = (call);                                                    \
@@ -143,6 +162,7 @@ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 // the opaque handle of the C ABI
 struct sb_sim {
     sb_params prm;
+    sb::DebugKnobs dbg;
     int device = 0;
     cudaStream_t stream = nullptr;
     sb::Geom g{};
@@ -178,6 +198,10 @@ struct sb_sim {
     double initial_norm_squared = 0.0;
     double pressure_range[2] = {0, 0}, speed_range[2] = {0, 0};
     double umax = 0.0, vmax = 0.0;  // max |u|, |v| over fluid cells (adaptive delt)
+    bool uvmax_valid = false;       // umax / vmax describe the current u, v and fluid set
+    // u_v_restore (src/grid/mod.rs:69) holds records: emptied by rebuild_boundary_list
+    // (:205), filled by set_boundary_u_and_v; set_u_and_v replays nothing while it is empty
+    bool restore_valid = false;
     uint32_t last_sor_iterations = 0;
     double last_norm_squared = 0.0;
     uint32_t sor_batch_hint = 0;

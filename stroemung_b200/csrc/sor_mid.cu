@@ -645,9 +645,8 @@ bool mid_plan(const sb_sim *s, MidPlan *pl) {
     if (nx < 3 || ny < 3 || nx > (1 << 20) || ny > (1 << 20)) return false;
     const size_t budget = (size_t)d.smem_optin - 1024;
     int want = std::min(d.sms, MID_MAX_CTAS), variant = 0;
-    if (const char *e = getenv("SB_SOR_MID_CTAS"))   // tests: force a decomposition ...
-        if (atoi(e) >= 1) want = std::min(want, atoi(e));
-    if (const char *e = getenv("SB_SOR_MID_VARIANT")) variant = atoi(e);   // ... and a kernel
+    if (s->dbg.sor_mid_ctas >= 1) want = std::min(want, s->dbg.sor_mid_ctas);   // tests: force a
+    variant = s->dbg.sor_mid_variant;                                        // decomposition / kernel
     // register window: column pairs on 512 threads, 4..8 rows per CTA (4 halo rows per side
     // must be own rows of the direct neighbour); more CTAs than asked for if bands get too tall
     if (variant != 1 && ny <= 2 * REG_THREADS && nx >= 4) {
@@ -704,8 +703,7 @@ sb_status launch_reg(const MidPlan &pl, MidParams &a, int smem_optin, cudaStream
 // grids this path takes: single GPU, not small enough for one SM, the whole of p, rhs and the
 // cell codes in the shared memory of the SMs together
 bool sor_mid_fits(const sb_sim *s) {
-    const char *e = getenv("SB_SOR_MID");  // 0 keeps such grids on the pass kernels (A/B, tests)
-    if (e && atoi(e) == 0) return false;
+    if (!s->dbg.sor_mid) return false;   // tests: keep such grids on the pass kernels
     if (s->slab) return false;
     MidPlan pl;
     return mid_plan(s, &pl);

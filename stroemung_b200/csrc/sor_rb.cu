@@ -625,15 +625,6 @@ sb_status ensure_tmaps(sb_sim *s) {
 
 int rb_halo_rows(int T) { return 2 * T + 2; }
 
-// SB_RB_STREAM=0 keeps every tile on the tile kernel (A/B measurements)
-static bool rb_stream_enabled() {
-    static int env = -1;
-    if (env < 0) {
-        const char *e = getenv("SB_RB_STREAM");
-        env = (e && atoi(e) == 0) ? 0 : 1;
-    }
-    return env != 0;
-}
 
 // one guarded pass: performs ctl->active_T sweeps from pbuf[ctl->src] into the other buffer
 // (norm_only: just the residual partial sums of pbuf[ctl->src]).  The all-fluid part of the
@@ -650,13 +641,13 @@ sb_status launch_sor_rb_pass(sb_sim *s, int *nparts_out, int norm_only, const Rb
     int ntiles = tiles_x * tiles_y;
     int n_tile = ntiles, n_items = 0;
     const int32_t *tile_list = nullptr;
-    if (!norm_only && rb_stream_enabled()) {
+    if (!norm_only && s->dbg.rb_stream) {
         if ((st = rb_ensure_plan(s, BX, BY, h))) return st;
         n_tile = s->plan.n_slow;
         n_items = s->plan.n_items;
         tile_list = s->plan.d_slow;
     }
-    const int n_frozen = (!norm_only && rb_stream_enabled()) ? s->plan.n_frozen : 0;
+    const int n_frozen = (!norm_only && s->dbg.rb_stream) ? s->plan.n_frozen : 0;
     const int nparts = n_tile + n_items + (n_frozen ? 1 : 0);
     size_t need = (size_t)nparts * TMAX + 64;
     if (need > s->partial_cap) {  // stream-ordered: no device-wide synchronisation

@@ -719,7 +719,7 @@ static void dump_trace(sb_sim *s) {
 }
 
 void rb_plan_release(sb_sim *s) {
-    if (getenv("SB_STREAM_TRACE") && s->plan.n_items) dump_trace(s);
+    if (s->dbg.trace_stream && s->plan.n_items) dump_trace(s);
     cudaFree(s->plan.d_slow);
     cudaFree(s->plan.d_items);
     cudaFree(s->plan.d_plain);
@@ -762,25 +762,10 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
         // half the rows (wall_weight) and fill ~8 SMs, which on a wide grid only breaks even
         // with leaving the wall tiles to the tile kernel; up to T = 3 it wins (0.343 vs
         // 0.394 ms per pass at 8192^2).  SB_RB_STREAM_KINDS overrides (A/B runs).
-        int keep = 3;   // T = 4 walls too since the row-granular plan below (was: T <= 3 ? 3 : 2)
-        if (const char *e = getenv("SB_RB_STREAM_KINDS")) keep = atoi(e);
+        const int keep = s->dbg.rb_stream_kinds;   // 3: everything (tests narrow it)
         for (auto &c : cls) {
             if (!(keep & 1) && (c & 3) != 1 + IT_PLAIN) c = 0;
             if (!(keep & 2) && (c & (TC_BC_LO | TC_BC_HI))) c = 0;
-        }
-    }
-    const char *edge_env = getenv("SB_SLAB_EDGE_TILES");
-    if (s->slab && edge_env && atoi(edge_env) == 1) {
-        // A/B: tiles that own rows within H of a slab edge on the tile kernel (its epilogue
-        // feeds the neighbour's halo rows too).  Default: the streaming kernel stores those
-        // rows into the neighbour's halo itself, and a plain channel needs no tile kernel
-        const int H = s->link.H;
-        for (int ti = 0; ti < tiles_x; ti++) {
-            const int64_t x0 = g.own0 + (int64_t)ti * BX, x1 = std::min<int64_t>(x0 + BX, g.own1);
-            const bool lo = s->link.lo_p[0] != nullptr && x0 < g.own0 + H;
-            const bool hi = s->link.hi_p[0] != nullptr && x1 > g.own1 - H;
-            if (lo || hi)
-                for (int tj = 0; tj < tiles_y; tj++) cls[(size_t)ti * tiles_y + tj] = 0;
         }
     }
     // runs of tiles of one item kind along x, per strip.  weight: how much longer a wall
@@ -794,7 +779,7 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
     // nothing on a wide grid (8192^2: 12.34 vs 12.40 ms) but 15 % on a narrow one (8192 x 2048:
     // 2 of 19 strips are walls), so it stays at 2 there.
     double wall_weight = s->slab ? 6.0 : 2.0;
-    if (const char *e = getenv("SB_WALL_WEIGHT")) wall_weight = atof(e);
+    if (s->dbg.wall_weight > 0.0) wall_weight = s->dbg.wall_weight;
     std::vector<Run> runs;
     std::vector<int32_t> slow;
     for (int tj = 0; tj < tiles_y; tj++) {
@@ -809,8 +794,7 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
     }
     std::vector<int32_t> frozen;
     {
-        const char *e = getenv("SB_RB_FROZEN");   // 0: frozen tiles stay on the tile kernel (A/B)
-        const bool use_frozen = !(e && atoi(e) == 0);
+        const bool use_frozen = s->dbg.rb_frozen;   // tests: frozen tiles on the tile kernel
         for (int t = 0; t < ntiles; t++) {
             if (cls[(size_t)t] != TC_FROZEN) continue;
             bool keep_frozen = use_frozen;
@@ -883,8 +867,7 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
     };
     std::vector<int> row_pieces;   // pieces per run; empty = keep the tile-granular plan
     {
-        const char *e = getenv("SB_RB_ROW_PLAN");
-        const bool enabled = !(e && atoi(e) == 0);
+        const bool enabled = true;
         int nrun[2] = {0, 0};
         for (const Run &r : runs) nrun[r.kind != IT_PLAIN]++;
         double best = best_cost;
@@ -1005,7 +988,7 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
         SB_CUDA(cudaMemcpyAsync(pl.d_items, items.data(), items.size() * sizeof(RbItem),
                                 cudaMemcpyHostToDevice, s->stream));
     SB_CUDA(cudaStreamSynchronize(s->stream));  // the vectors go out of scope
-    if (getenv("SB_DEBUG_PLAN")) {
+    if (s->dbg.trace_plan) {
         int nk[3] = {0, 0, 0}, nbc = 0, longest = 0;
         for (const RbItem &it : items) {
             if (it.x1 <= it.x0) continue;
@@ -1052,7 +1035,7 @@ sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h,
     pe.pbuf = rb_pbuf_ptr(s);
     pe.ctl = s->d_ctl;
     static int trace_set = 0;
-    if (!trace_set && getenv("SB_STREAM_TRACE")) {
+    if (!trace_set && s->dbg.trace_stream) {
         const int one = 1;
         cudaMemcpyToSymbol(g_trace_on, &one, sizeof(int));
         trace_set = 1;

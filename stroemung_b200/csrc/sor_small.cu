@@ -137,9 +137,7 @@ sor_small_kernel(Geom g, double *const *__restrict__ pbuf, const double *__restr
 
 // grids this path takes: single GPU, everything in one CTA's shared memory
 bool sor_small_fits(const sb_sim *s) {
-    const char *e = getenv("SB_SOR_SMALL");  // 0 keeps small grids on the pass kernels (A/B, tests)
-    const bool enabled = !(e && atoi(e) == 0);
-    return enabled && !s->slab && s->g.NX >= 3 && s->g.NY >= 3 && s->g.NX * s->g.NY <= 12288;
+    return s->dbg.sor_small && !s->slab && s->g.NX >= 3 && s->g.NY >= 3 && s->g.NX * s->g.NY <= 12288;
 }
 
 // the whole solve; the host has initialised *d_ctl (src, max_iterations) and reads it back

@@ -708,6 +708,7 @@ sb_status launch_velocity_bc(sb_sim *s) {
     velocity_bc_gather<<<nb, TPB, 0, s->stream>>>(s->g, s->u, s->v, s->cflag, s->bl, row0, row1);
     velocity_bc_scatter<<<nb, TPB, 0, s->stream>>>(s->g, s->u, s->v, s->bl, row0, row1);
     s->launches += 2;
+    s->restore_valid = true;
     SB_CUDA(cudaGetLastError());
     return SB_OK;
 }
@@ -846,7 +847,7 @@ sb_status launch_adapt_uv(sb_sim *s, int with_prange) {
             s->g, s->p[s->cur], s->f, s->gq, s->cflag, s->u, s->v, s->d_partial, s->prm.delt,
             s->prm.delx, s->prm.dely);
     s->launches++;
-    if (s->bl.n) {
+    if (s->bl.n && s->restore_valid) {   // u_v_restore is empty until the first velocity BC
         int nb = (int)((s->bl.n + TPB - 1) / TPB);
         restore_uv_kernel<<<nb, TPB, 0, s->stream>>>(s->g, s->u, s->v, s->bl);
         s->launches++;
@@ -868,6 +869,7 @@ sb_status launch_adapt_uv(sb_sim *s, int with_prange) {
     s->speed_range[1] = sqrt(out[1]);
     s->umax = out[2];
     s->vmax = out[3];
+    s->uvmax_valid = true;
     if (with_prange) {
         s->pressure_range[0] = out[4];
         s->pressure_range[1] = out[5];
@@ -905,6 +907,7 @@ sb_status launch_speed_range(sb_sim *s) {
     s->speed_range[1] = sqrt(out[1]);
     s->umax = out[2];
     s->vmax = out[3];
+    s->uvmax_valid = true;
     return SB_OK;
 }
 

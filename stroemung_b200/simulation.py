@@ -287,6 +287,18 @@ class Simulation:
         st = self._state()
         return st.initial_norm_squared if st.has_initial_norm else None
 
+    @initial_norm_squared.setter
+    def initial_norm_squared(self, value):
+        """pub initial_norm_squared: Option<Real> (src/simulation.rs:62); None makes the next
+        solve_sor latch the norm after its first sweep (:229-237, :276)"""
+        st = self._state()
+        self._prm.time, self._prm.iterations = st.time, st.iterations
+        if self._prm.tau > 0:
+            self._prm.delt = st.delt
+        self._prm.has_initial_norm = 0 if value is None else 1
+        self._prm.initial_norm_squared = 0.0 if value is None else value
+        self._check(_capi.lib().sb_set_params(self._h, C.byref(self._prm)))
+
     f = property(lambda s: s.grid._get(_capi.FIELD_F), lambda s, v: s.grid._set(_capi.FIELD_F, v))
     g = property(lambda s: s.grid._get(_capi.FIELD_G), lambda s, v: s.grid._set(_capi.FIELD_G, v))
     rhs = property(lambda s: s.grid._get(_capi.FIELD_RHS),
