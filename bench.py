@@ -281,11 +281,14 @@ def verify_on_bench_grid(wl, mode, tblock, device, sweeps=8, tick_sweeps=4):
                gamma=wl["gamma"], reynolds=wl["reynolds"], sor_absolute_epsilon=wl["eps"],
                max_iterations=tick_sweeps, omega=wl["omega"])
     rb = mode == "rb"
+    # initial_norm_squared = 0: the tick runs all `tick_sweeps` sweeps (with the norm of the
+    # random state latched, the exit rule of src/simulation.rs:279 would fire after one)
     o = po.OracleSim(nx, ny, kind=g["kind"], bu=g["bu"], bv=g["bv"], p=p, u=u, v=v,
+                     initial_norm_squared=0.0,
                      sor_mode=po.SOR_RED_BLACK if rb else po.SOR_REFERENCE_ORDER, **prm)
     unf = {"size": (nx, ny), "cell_size": wl["cell_size"], "delt": wl["delt"],
            "gamma": wl["gamma"], "reynolds": wl["reynolds"], "sor_absolute_epsilon": wl["eps"],
-           "max_iterations": tick_sweeps, "omega": wl["omega"],
+           "max_iterations": tick_sweeps, "omega": wl["omega"], "initial_norm_squared": 0.0,
            "grid": {"p": p, "u": u, "v": v, "kind": g["kind"], "bu": g["bu"], "bv": g["bv"]}}
     sim = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK if rb else SOR_REFERENCE_ORDER,
                               temporal_block=tblock, device=device)
@@ -390,10 +393,12 @@ def run_ours(args):
     sampler.begin()
     sim.timer_begin()                         # CUDA event on the stream the kernels run on
     sor_ms = 0.0
+    stage_ms = np.zeros(4)
     for _ in range(args.steps):
         it, nrm = sim.run_simulation_tick()   # synchronises the handle's stream at its end
         sweeps.append(it)
         sor_ms += sim.last_sor_ms
+        stage_ms += sim.last_stage_ms
     dt = sim.timer_end() * 1e-3               # event + synchronize
     sampler.end()
     barrier()
@@ -523,6 +528,8 @@ def run_ours(args):
                 "algorithmic_gbs": SOR_BYTES_PER_CELL_SWEEP * cells * total_sweeps /
                 (sor_ms * 1e-3) / 1e9 if sor_ms else None,
                 "ms_per_tick": sor_ms / max(args.steps, 1)},
+        "stage_ms_per_tick": dict(zip(("velocity_bc", "fg_rhs", "sor", "set_u_and_v"),
+                                      (float(x) / max(args.steps, 1) for x in stage_ms))),
         "tick_roofline": {"bytes_per_cell": kfix + SOR_BYTES_PER_CELL_SWEEP * k_avg,
                           "roofline_mcell_steps_per_s": n_gpus * peak * 1e9 /
                           (kfix + SOR_BYTES_PER_CELL_SWEEP * k_avg) / 1e6,

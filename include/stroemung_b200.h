@@ -248,6 +248,11 @@ uint64_t sb_kernel_launches(const sb_sim *sim);
 /* device time (ms) of the SOR solve inside the last sb_tick / sb_solve_sor / sb_sor_sweeps,
  * measured with CUDA events on the handle's stream */
 double sb_last_sor_ms(const sb_sim *sim);
+/* device time (ms, CUDA events on the handle's stream) of the four stages of the last sb_tick,
+ * in the order of run_simulation_tick (/root/reference/src/simulation.rs:324-333):
+ * ms[0] set_boundary_u_and_v, ms[1] calculate_f_and_g + calculate_rhs, ms[2] solve_sor,
+ * ms[3] set_u_and_v (+ ranges) */
+sb_status sb_last_stage_ms(sb_sim *sim, double ms[4]);
 /* how the last red-black pass split the grid: tiles on the tile kernel (walls, obstacles,
  * grid ring, slab edges) and work items of the streaming kernel (all-fluid regions) */
 sb_status sb_rb_plan(const sb_sim *sim, int32_t *tile_kernel_tiles, int32_t *stream_items);

@@ -420,16 +420,90 @@ int so_set_boundary_u_and_v(so_sim *s) {
 /* ------------------------------------------------------------------ */
 /* F, G, RHS: src/simulation.rs:122-214                                */
 /* ------------------------------------------------------------------ */
+/* EXTENSION (performance mode, SO_SOR_RED_BLACK only; not in the reference): F, G and RHS
+ * with the kernels' arithmetic -- the formulas of src/math.rs:19-174 and
+ * src/simulation.rs:349-392, 204-214 with every division replaced by a multiplication with a
+ * reciprocal computed once per run and a*b+c taken fused where the kernel does (explicit
+ * fma(); this file is built with -ffp-contract=off, so nothing else contracts).  The GPU
+ * kernel (stages.cu, fgr_cell_fast) evaluates the same tree: bit-identical.  Against the
+ * strict formulas the values differ in the last bits only; like the red-black ordering this
+ * is covered by the performance-mode tolerance (converged fields within the SOR eps). */
+typedef struct {
+    double rdx2, rdy2, r4dx, r4dy, rre, rdx, rdy, rdt, gamma, delt;
+} fg_fast_consts;
+
+static fg_fast_consts fg_fast_constants(const so_sim *s) {
+    fg_fast_consts k;
+    const double dx = s->prm.delx, dy = s->prm.dely;
+    k.rdx2 = 1.0 / (dx * dx);
+    k.rdy2 = 1.0 / (dy * dy);
+    k.r4dx = 1.0 / (4.0 * dx);
+    k.r4dy = 1.0 / (4.0 * dy);
+    k.rre = 1.0 / s->prm.reynolds;
+    k.rdx = 1.0 / dx;
+    k.rdy = 1.0 / dy;
+    k.rdt = 1.0 / s->prm.delt;
+    k.gamma = s->prm.gamma;
+    k.delt = s->prm.delt;
+    return k;
+}
+
+/* laplacian: rdx2*((e - 2c) + w) + rdy2*((s - 2c) + n) */
+static inline double lap_fast(const fg_fast_consts *k, double c, double n, double s_, double w,
+                              double e) {
+    const double tc = 2.0 * c;
+    return fma(k->rdx2, (e - tc) + w, k->rdy2 * ((s_ - tc) + n));
+}
+
+/* numerator of a donor-cell term: (a*pa - b*pb) + gamma*(|a|*da - |b|*db) */
+static inline double donor_fast(const fg_fast_consts *k, double a, double pa, double b,
+                                double pb, double da, double db) {
+    const double left = fma(a, pa, -(b * pb));
+    const double d = fma(fabs(a), da, -(fabs(b) * db));
+    return fma(k->gamma, d, left);
+}
+
+static inline void fg_cell_fast(const fg_fast_consts *k, const double u[9], const double v[9],
+                                double *f, double *g) {
+    const double u_c = B(u, 1, 1), u_n = B(u, 1, 0), u_s = B(u, 1, 2), u_w = B(u, 0, 1),
+                 u_e = B(u, 2, 1), u_sw = B(u, 0, 2);
+    const double v_c = B(v, 1, 1), v_n = B(v, 1, 0), v_s = B(v, 1, 2), v_w = B(v, 0, 1),
+                 v_e = B(v, 2, 1), v_ne = B(v, 2, 0);
+    /* du2dx: a = u_c + u_e, b = u_w + u_c */
+    const double a1 = u_c + u_e, b1 = u_w + u_c;
+    const double x_f = donor_fast(k, a1, a1, b1, b1, u_c - u_e, u_w - u_c);
+    /* duvdy: a = v_c + v_e, b = v_n + v_ne */
+    const double a2 = v_c + v_e, b2 = v_n + v_ne;
+    const double y_f = donor_fast(k, a2, u_c + u_s, b2, u_n + u_c, u_c - u_s, u_n - u_c);
+    /* duvdx: a = u_c + u_s, b = u_w + u_sw */
+    const double a3 = u_c + u_s, b3 = u_w + u_sw;
+    const double x_g = donor_fast(k, a3, v_c + v_e, b3, v_w + v_c, v_c - v_e, v_w - v_c);
+    /* dv2dy: a = v_c + v_s, b = v_n + v_c */
+    const double a4 = v_c + v_s, b4 = v_n + v_c;
+    const double y_g = donor_fast(k, a4, a4, b4, b4, v_c - v_s, v_n - v_c);
+    const double lu = lap_fast(k, u_c, u_n, u_s, u_w, u_e);
+    const double lv = lap_fast(k, v_c, v_n, v_s, v_w, v_e);
+    /* F = u + dt*(lap(u)/Re - du2dx - duvdy), the divisions by 4dx / 4dy folded in */
+    *f = fma(k->delt, fma(-k->r4dy, y_f, fma(-k->r4dx, x_f, k->rre * lu)), u_c);
+    *g = fma(k->delt, fma(-k->r4dy, y_g, fma(-k->r4dx, x_g, k->rre * lv)), v_c);
+}
+
 void so_calculate_f_and_g(so_sim *s) {
     const uint64_t nx = s->nx, ny = s->ny;
     const double delx = s->prm.delx, dely = s->prm.dely, delt = s->prm.delt,
                  gamma = s->prm.gamma, re = s->prm.reynolds;
+    const int fast = s->prm.sor_mode == SO_SOR_RED_BLACK;
+    const fg_fast_consts kf = fg_fast_constants(s);
     if (nx >= 3 && ny >= 3) {
         for (uint64_t x = 1; x + 1 < nx; x++) {
             for (uint64_t y = 1; y + 1 < ny; y++) {
                 double ub[9], vb[9];
                 gather3x3(s->u, ny, x, y, ub);
                 gather3x3(s->v, ny, x, y, vb);
+                if (fast) {
+                    fg_cell_fast(&kf, ub, vb, &s->f[IDX(s, x, y)], &s->g[IDX(s, x, y)]);
+                    continue;
+                }
                 s->f[IDX(s, x, y)] = so_calculate_f(ub, vb, delx, dely, delt, gamma, re);
                 s->g[IDX(s, x, y)] = so_calculate_g(ub, vb, delx, dely, delt, gamma, re);
             }
@@ -455,6 +529,17 @@ void so_calculate_f_and_g(so_sim *s) {
 void so_calculate_rhs(so_sim *s) {
     const uint64_t nx = s->nx, ny = s->ny;
     const double delx = s->prm.delx, dely = s->prm.dely, delt = s->prm.delt;
+    if (s->prm.sor_mode == SO_SOR_RED_BLACK) { /* extension: performance-mode arithmetic */
+        const fg_fast_consts k = fg_fast_constants(s);
+        for (uint64_t x = 1; x < nx; x++) {
+            for (uint64_t y = 1; y < ny; y++) {
+                uint64_t c = IDX(s, x, y);
+                s->rhs[c] = k.rdt * fma(k.rdx, s->f[c] - s->f[c - ny],
+                                        k.rdy * (s->g[c] - s->g[c - 1]));
+            }
+        }
+        return;
+    }
     for (uint64_t x = 1; x < nx; x++) {
         for (uint64_t y = 1; y < ny; y++) {
             uint64_t c = IDX(s, x, y);

@@ -70,7 +70,7 @@ SYMBOLS = [
     "sb_edit_cells", "sb_render_rgba", "sb_create_preset", "sb_error_cell", "sb_last_error_string",
     "sb_slab_export", "sb_slab_connect", "sb_slab_sync_halos", "sb_du2dx", "sb_duvdx", "sb_duvdy",
     "sb_dv2dy", "sb_laplacian", "sb_residual", "sb_calculate_f", "sb_calculate_g",
-    "sb_profile_enable", "sb_profile_read", "sb_timer_begin", "sb_timer_end", "sb_kernel_launches", "sb_last_sor_ms", "sb_stream",
+    "sb_profile_enable", "sb_profile_read", "sb_timer_begin", "sb_timer_end", "sb_kernel_launches", "sb_last_sor_ms", "sb_last_stage_ms", "sb_stream",
     "sb_rb_plan", "sb_last_sor_path",
     "sb_version",
 ]
@@ -134,6 +134,7 @@ def lib():
         "sb_rb_plan": ([vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)], C.c_int),
         "sb_last_sor_path": ([vp, C.POINTER(C.c_int32)], C.c_int32),
         "sb_last_sor_ms": ([vp], C.c_double),
+        "sb_last_stage_ms": ([vp, dp], C.c_int),
         "sb_stream": ([vp], vp),
         "sb_version": ([], C.c_char_p),
     }

@@ -100,6 +100,8 @@ static void destroy(sb_sim *s) {
     if (s->ev_sor1) cudaEventDestroy(s->ev_sor1);
     if (s->ev_t0) cudaEventDestroy(s->ev_t0);
     if (s->ev_t1) cudaEventDestroy(s->ev_t1);
+    for (cudaEvent_t e : s->ev_stage)
+        if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -187,6 +189,7 @@ static sb_status allocate(const sb_params *params, sb_sim **out) {
     SB_TRY(cudaEventCreate(&s->ev_sor1));
     SB_TRY(cudaEventCreate(&s->ev_t0));
     SB_TRY(cudaEventCreate(&s->ev_t1));
+    for (cudaEvent_t &e : s->ev_stage) SB_TRY(cudaEventCreate(&e));
     if (params->world > 1 && slab_prepare(s) != SB_OK) {
         destroy(s);
         return SB_CUDA_ERROR;
@@ -442,11 +445,16 @@ static sb_status tick(sb_sim *s, uint32_t *iters, double *norm) {
         if (!s->uvmax_valid && (st = launch_speed_range(s))) return st;
         adapt_delt(s);
     }
+    cudaEventRecord(s->ev_stage[0], s->stream);
     if ((st = launch_velocity_bc(s))) return st;
+    cudaEventRecord(s->ev_stage[1], s->stream);
     if ((st = launch_fg_rhs(s, 3))) return st;
+    cudaEventRecord(s->ev_stage[2], s->stream);
     int prange_due = 0;
     if ((st = solve(s, s->prm.max_iterations, 1, iters, norm, nullptr, &prange_due))) return st;
+    cudaEventRecord(s->ev_stage[3], s->stream);
     if ((st = launch_adapt_uv(s, prange_due))) return st;
+    cudaEventRecord(s->ev_stage[4], s->stream);
     s->time += s->prm.delt;
     s->iterations += 1;
     s->last_sor_iterations = *iters;
@@ -988,6 +996,17 @@ int32_t sb_last_sor_path(const sb_sim *sim, int32_t *ctas) {
     return sim->last_sor_path;
 }
 double sb_last_sor_ms(const sb_sim *sim) { return sim ? sim->last_sor_ms : 0.0; }
+sb_status sb_last_stage_ms(sb_sim *sim, double ms[4]) {
+    SB_ENTER(sim);
+    if (!ms) return SB_INVALID_ARGUMENT;
+    SB_CUDA(cudaStreamSynchronize(sim->stream));
+    for (int i = 0; i < 4; i++) {
+        float t = 0.f;
+        ms[i] = cudaEventElapsedTime(&t, sim->ev_stage[i], sim->ev_stage[i + 1]) == cudaSuccess ? t : 0.0;
+    }
+    cudaGetLastError();   // events never recorded (no tick yet): zeros, not an error
+    return SB_OK;
+}
 void *sb_stream(const sb_sim *sim) { return sim ? (void *)sim->stream : nullptr; }
 const char *sb_version(void) { return "stroemung_b200 0.1.0 (sm_100a)"; }
 

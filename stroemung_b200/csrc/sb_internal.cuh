@@ -209,6 +209,7 @@ struct sb_sim {
     uint8_t err_kind = 0;
     uint64_t launches = 0;
     cudaEvent_t ev_sor0 = nullptr, ev_sor1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_stage[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // sb_last_stage_ms
     double last_sor_ms = 0.0;
     // optional per-pass event profiling (sb_profile_enable)
     bool profiling = false;

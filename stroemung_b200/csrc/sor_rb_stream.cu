@@ -64,6 +64,10 @@ constexpr int IT_BC_HI = 8;    // the item's last row is a boundary row fed from
 // tile classes of rb_class_kernel: 0 = tile kernel, 1 + item kind otherwise, plus
 constexpr int TC_BC_LO = 4, TC_BC_HI = 8;  // the tile owns grid row 0 / NX-1 as such a row
 constexpr int TC_FROZEN = 16;  // not streamable, but nothing in or next to the tile ever changes
+// the footprint reaches grid row NX-1 without the tile owning it (the last tile row of the
+// lattice is shorter than the halo): streamable only as part of a run that goes on into the
+// next tile, whose item then owns that boundary row
+constexpr int TC_NEED_NEXT = 32;
 
 // Everything that indexes a ring is a compile-time constant inside the unrolled window:
 //   * the tick loop is unrolled over NW = 2T+4 ticks (the register window), U = tick mod NW;
@@ -193,6 +197,9 @@ template <int T, bool STEADY, int WALL, int SET, bool RED>
 __device__ __forceinline__ void half_sweep(double (&W)[2 * T + 4][4], const int s, const int q,
                                            const int kk, const double rha, const double rhb,
                                            double &acc_a, double &acc_b, const SCtx &c) {
+#ifdef SB_STREAM_NOCOMPUTE   // experiment: the memory pipeline of the pass alone (wrong results)
+    return;
+#endif
     constexpr int NW = stream_nw(T);
     constexpr int ia = SET, ib = SET + 2, oa = SET ^ 1, ob = (SET ^ 1) + 2;
     // the wall cell is one of these cells / the fluid cell next to the wall is
@@ -343,7 +350,11 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
         const int lag = 2 * T + 1;
         const int s = (U + 2 * NW - lag) % NW, sm = (s + NW - 1) % NW, sp = (s + 1) % NW;
         const int q = R - lag;
+#ifdef SB_STREAM_NOCOMPUTE
+        if (false) {
+#else
         if (STEADY || (unsigned)(q - c.cx0) < (unsigned)(c.cx1 - c.cx0)) {  // warp-uniform
+#endif
             double na, nb, ra, rb;
             if ((s & 1) == 0) {
                 nbr2<0>(c, W[s], na, nb);
@@ -623,7 +634,7 @@ __global__ void rb_class_kernel(const uint8_t *__restrict__ cflag, Geom g, int t
     // the owned columns of the last tile column need h columns of strip to their left
     if (kind == IT_WALL_HI && (int64_t)tj * BY - c0 < h) ok = 0;
     if (kind == IT_PLAIN && (col < 1 || col > g.NY - 2)) ok = 0;
-    int bc_lo = 0, bc_hi = 0;
+    int bc_lo = 0, bc_hi = 0, need_next = 0;
     if (ok) {
         for (int64_t r = x0 - h; r < x1 + h; r++) {
             const int64_t gx = g.gx0 + r;
@@ -633,9 +644,10 @@ __global__ void rb_class_kernel(const uint8_t *__restrict__ cflag, Geom g, int t
             if (gx == 0 || gx == g.NX - 1) {
                 // a boundary row: must be owned by this tile and be fed from the row inside
                 const int want = gx == 0 ? SB_EDGE_E : SB_EDGE_W;
-                if (r < x0 || r >= x1 || !cf_is_boundary(f) ||
-                    cf_edge(f) != (wall_col ? SB_EDGE_NONE : want)) { ok = 0; break; }
-                if (gx == 0) bc_lo = 1; else bc_hi = 1;
+                if (!cf_is_boundary(f) || cf_edge(f) != (wall_col ? SB_EDGE_NONE : want)) { ok = 0; break; }
+                if (r >= x0 && r < x1) { if (gx == 0) bc_lo = 1; else bc_hi = 1; }
+                else if (gx == g.NX - 1 && r >= x1) need_next = 1;   // owned by the next tile
+                else { ok = 0; break; }
             } else if (wall_col) {
                 if (!cf_is_boundary(f) ||
                     cf_edge(f) != (kind == IT_WALL_LO ? SB_EDGE_S : SB_EDGE_N)) { ok = 0; break; }
@@ -661,7 +673,8 @@ __global__ void rb_class_kernel(const uint8_t *__restrict__ cflag, Geom g, int t
     }
     frozen = __syncthreads_and(frozen);
     if (threadIdx.x == 0)
-        cls[tile] = ok ? (uint8_t)(1 + kind + (bc_lo ? TC_BC_LO : 0) + (bc_hi ? TC_BC_HI : 0))
+        cls[tile] = ok ? (uint8_t)(1 + kind + (bc_lo ? TC_BC_LO : 0) + (bc_hi ? TC_BC_HI : 0) +
+                                   (need_next ? TC_NEED_NEXT : 0))
                        : (frozen ? (uint8_t)TC_FROZEN : (uint8_t)0);
 }
 
@@ -768,6 +781,15 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
             if (!(keep & 2) && (c & (TC_BC_LO | TC_BC_HI))) c = 0;
         }
     }
+    // a tile that needs its successor in the same run (TC_NEED_NEXT) and does not get it
+    // stays with the tile kernel
+    for (int tj = 0; tj < tiles_y; tj++)
+        for (int ti = tiles_x - 1; ti >= 0; ti--) {
+            uint8_t &c = cls[(size_t)ti * tiles_y + tj];
+            if (c == TC_FROZEN || !(c & TC_NEED_NEXT)) continue;
+            const uint8_t nxt = ti + 1 < tiles_x ? cls[(size_t)(ti + 1) * tiles_y + tj] : (uint8_t)0;
+            if (nxt == TC_FROZEN || (nxt & 3) != (c & 3)) c = 0;
+        }
     // runs of tiles of one item kind along x, per strip.  weight: how much longer a wall
     // strip takes per row than a plain one; its items get that much fewer rows
     struct Run { int tj, ti0, len, kind; double weight; };
@@ -923,8 +945,17 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
         const bool by_rows = !row_pieces.empty();
         const int m = by_rows ? row_pieces[ri] : pieces(r, best_seg);
         const int64_t rx0 = g.own0 + (int64_t)r.ti0 * BX, rrows = run_rows(r);
+        // tile-granular cuts: never between a TC_NEED_NEXT tile and its successor (the cut
+        // moves one tile down; the row-granular pieces are >= BX rows long and cannot end
+        // within the halo of the boundary row they do not own)
+        auto cut = [&](int i) {
+            int c = (int)((int64_t)r.len * i / m);
+            if (c > 0 && c < r.len && (cls[(size_t)(r.ti0 + c - 1) * tiles_y + r.tj] & TC_NEED_NEXT)) c--;
+            return c;
+        };
         for (int i = 0; i < m; i++) {
-            const int a = (int)((int64_t)r.len * i / m), b = (int)((int64_t)r.len * (i + 1) / m);
+            const int a = cut(i), b = cut(i + 1);
+            if (!by_rows && a >= b) continue;
             RbItem it;
             if (by_rows) {
                 const int64_t ra = i == 0 ? 0 : (rrows * i / m) & ~(int64_t)1;

@@ -327,17 +327,149 @@ fg_rhs_kernel(Geom g, const double *__restrict__ u, const double *__restrict__ v
     }
 }
 
+// ---- K2, performance mode: the same stage with the FgFast arithmetic (cellops.cuh) -----------
+// Same decomposition as fg_rhs_kernel (one warp = 31 output columns + a helper lane, marching
+// along x), rebuilt around the ~70 FP64 instructions per cell that are left once the exact
+// divisions are gone -- at that size the bookkeeping of the strict kernel (window slide,
+// per-cell role tests: 310 of its 377 instructions in this mode) would dominate:
+//   * the 3-row window rotates by NAME (the row loop is unrolled 4x), nothing is copied;
+//   * a row whose 32 cells are all fluid cells without a non-fluid neighbour (flag bit
+//     CF_NEAR clear) inside the stencil range takes a straight-line path: no role tests, no
+//     flag of any neighbour is read; everything else (walls, obstacles, the ring, slab
+//     edges) takes the general path with the reference's overwrite rules
+//     (src/simulation.rs:167-201);
+//   * the row two ahead is requested before the current one is computed.
+constexpr int FGF_ROWS = 64;
+constexpr int FGF_WARPS = 8;
+constexpr int FGF_COLS = 31 * FGF_WARPS;
+#ifndef FGF_MINB
+#define FGF_MINB 2
+#endif
+#ifndef FGF_PF
+#define FGF_PF 1   // rows requested ahead of the stencil window
+#endif
+
+struct FgRow {
+    double un, uc, us, vn, vc, vs;
+    unsigned fl;   // flag byte of (row, y); 0 outside the local rows
+};
+
+__global__ void __launch_bounds__(32 * FGF_WARPS, FGF_MINB)
+fg_rhs_fast_kernel(Geom g, const double *__restrict__ u, const double *__restrict__ v,
+                   const uint8_t *__restrict__ cflag, double *__restrict__ f,
+                   double *__restrict__ gq, double *__restrict__ rhs, int fg_row0, int row1,
+                   FgFast kf, int write_fg, int write_rhs) {
+    // 32-bit row / column arithmetic (rows and columns are < 2^31; the launcher checks);
+    // 64-bit only in the row base pointers, which advance by one pitch per step
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NY = (int)g.NY, NX = (int)g.NX, nxl = (int)g.nxl, gx0 = (int)g.gx0;
+    const int y = (int)blockIdx.y * FGF_COLS - 1 + warp * 31 + lane;
+    const int xs = fg_row0 + (int)blockIdx.x * FGF_ROWS;  // first output row
+    const int xe = min(xs + FGF_ROWS, row1);
+    if (y - lane >= NY) return;  // warp-uniform: nothing of this warp is inside the grid
+    const bool y_ok = y >= 0 && y < NY;
+    const bool out_lane = lane >= 1 && y_ok;
+    const bool y_int = y >= 1 && y <= NY - 2;
+    // clamped column indices: loads stay inside the row; a clamped value is never used by a
+    // cell that takes the stencil (those have all eight neighbours)
+    const int yc = min(max(y, 0), NY - 1);
+    const int yn = max(yc - 1, 0), ys = min(yc + 1, NY - 1);
+    const bool has_s = y + 1 < NY;
+    const int last = nxl - 1;
+    const int64_t pitch = g.pitch;
+
+    // the pre-row (xs - 1) is needed when this strip produces rhs for row xs
+    const bool pre = write_rhs && xs - 1 >= 0;
+    const int x_first = pre ? xs - 1 : xs;
+    // row `lr` = the next row to load, clamped to the local rows; its base offset
+    int lr = x_first - 1;
+    int64_t lro = (int64_t)min(max(lr, 0), last) * pitch;
+    auto load_row = [&](FgRow &r) {
+        const double *ur = u + lro, *vr = v + lro;
+        r.un = ur[yn]; r.uc = ur[yc]; r.us = ur[ys];
+        r.vn = vr[yn]; r.vc = vr[yc]; r.vs = vr[ys];
+        r.fl = (unsigned)lr <= (unsigned)last ? (unsigned)cflag[lro + yc] : 0u;
+        lro += (lr >= 0 && lr < last) ? pitch : 0;   // the clamp, kept incrementally
+        lr++;
+    };
+    // FGF_PF rows are in flight ahead of the three the stencil uses; the window rotates by
+    // NAME (the row loop is unrolled over its NS slots), nothing is copied
+    constexpr int NS = 3 + FGF_PF;
+    FgRow W[NS];   // slot k of step i holds row x - 1 + ((k - i) mod NS)
+#pragma unroll
+    for (int k = 0; k < NS - 1; k++) load_row(W[k]);
+    double f_west = 0.0;  // final f of (x-1, y)
+    int64_t c = (int64_t)x_first * pitch + yc;   // (x, y) of the row being computed
+    for (int x0 = x_first; x0 < xe; x0 += NS) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            // rows past xe (the tail of the last group) are computed from clamped loads and
+            // never stored
+            const int x = x0 + i;
+            FgRow &A = W[i % NS], &B = W[(i + 1) % NS], &C = W[(i + 2) % NS];
+            load_row(W[(i + NS - 1) % NS]);   // row x + 1 + FGF_PF
+            const int gx = gx0 + x;
+            const bool row_int = gx >= 1 && gx <= NX - 2;
+            const unsigned fl = B.fl;
+            Stencil9 su, sv;
+            su.nw = A.un; su.w = A.uc; su.sw = A.us;
+            su.n = B.un;  su.c = B.uc; su.s = B.us;
+            su.ne = C.un; su.e = C.uc; su.se = C.us;
+            sv.nw = A.vn; sv.w = A.vc; sv.sw = A.vs;
+            sv.n = B.vn;  sv.c = B.vc; sv.s = B.vs;
+            sv.ne = C.vn; sv.e = C.vc; sv.se = C.vs;
+            // the stencil values, needed or not (one copy of the arithmetic)
+            double fv = calculate_f_fast(su, sv, kf);
+            double gv = calculate_g_fast(su, sv, kf);
+            bool valid = true, st_f = true, st_g = true;
+            // a fluid cell with four fluid neighbours: valid, kind 0, CF_NEAR clear
+            const bool plain = row_int && y_int && (fl & 0x8fu) == (unsigned)CF_FLUID;
+            if (!__all_sync(0xffffffffu, plain)) {   // rare: walls, obstacles, ring, slab edges
+                valid = y_ok && (fl & CF_VALID);
+                if (!valid) {
+                    fv = gv = 0.0;
+                    st_f = st_g = false;
+                } else if (!cf_is_fluid((uint8_t)fl)) {
+                    fv = B.uc;
+                    gv = B.vc;
+                } else {
+                    const bool interior = row_int && y_int;
+                    const bool east_solid = gx + 1 < NX && x + 1 < nxl &&
+                                            !cf_is_fluid((uint8_t)C.fl);
+                    const bool in_rows = (unsigned)x <= (unsigned)last;
+                    const uint8_t fl_s = (has_s && in_rows) ? cflag[c + 1] : (uint8_t)0;
+                    const bool south_solid = has_s && !cf_is_fluid(fl_s);
+                    if (east_solid) fv = B.uc;
+                    else if (!interior) { fv = in_rows ? f[c] : 0.0; st_f = false; }  // fluid ring cell
+                    if (south_solid) gv = B.vc;
+                    else if (!interior) { gv = in_rows ? gq[c] : 0.0; st_g = false; }
+                }
+            }
+            const double g_north = __shfl_up_sync(0xffffffffu, gv, 1);
+            if (x >= xs && x < xe && out_lane && valid) {  // not the pre-row, not the tail
+                if (write_fg && st_f) f[c] = fv;
+                if (write_fg && st_g) gq[c] = gv;
+                if (write_rhs && gx >= 1 && y >= 1)
+                    rhs[c] = rhs_fast(kf, fv, f_west, gv, g_north);
+            }
+            f_west = fv;
+            c += pitch;
+        }
+    }
+}
+
 // RHS on its own (sb_calculate_rhs): reads f, g from memory
 __global__ void rhs_kernel(Geom g, const double *__restrict__ f, const double *__restrict__ gq,
                            double *__restrict__ rhs, int64_t row0, int64_t row1, DivC dx,
-                           DivC dy, DivC dt) {
+                           DivC dy, DivC dt, int fast, FgFast kf) {
     int64_t y = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     int64_t lx = row0 + blockIdx.x;
     if (y < 1 || y >= g.NY || lx >= row1) return;
     int64_t gx = g.gx0 + lx;
     if (gx < 1 || gx >= g.NX) return;
     int64_t c = lx * g.pitch + y;
-    rhs[c] = dt(dx(f[c] - f[c - g.pitch]) + dy(gq[c] - gq[c - 1]));
+    if (fast) rhs[c] = rhs_fast(kf, f[c], f[c - g.pitch], gq[c], gq[c - 1]);
+    else rhs[c] = dt(dx(f[c] - f[c - g.pitch]) + dy(gq[c] - gq[c - 1]));
 }
 
 // ---- K3: pressure BC over the boundary list (reads fluid cells, writes boundary cells) ---
@@ -745,11 +877,22 @@ sb_status launch_fg_rhs(sb_sim *s, int what) {
     const bool with_rhs = (what & 2) != 0;
     // slab mode without the fused rhs: F of the halo row in front is stored for rhs_kernel
     int64_t row0 = (s->halo && !with_rhs) ? s->g.own0 - 1 : s->g.own0, row1 = s->g.own1;
-    dim3 grid((unsigned)((row1 - row0 + FGR_ROWS - 1) / FGR_ROWS),
-              (unsigned)((s->g.NY + FGR_COLS - 1) / FGR_COLS));
-    fg_rhs_kernel<<<grid, 32 * FGR_WARPS, 0, s->stream>>>(
-        s->g, s->u, s->v, s->cflag, s->f, s->gq, s->rhs, row0, row1, s->g.own0, fgr_consts(s), 1,
-        with_rhs ? 1 : 0);
+    const sb_params &p = s->prm;
+    // performance mode (red-black): reciprocal + FMA arithmetic, bit-identical to the oracle's
+    // restatement of it; reference-order mode: the reference's exact divisions
+    if (p.sor_mode == SB_SOR_RED_BLACK) {
+        dim3 grid((unsigned)((row1 - row0 + FGF_ROWS - 1) / FGF_ROWS),
+                  (unsigned)((s->g.NY + FGF_COLS - 1) / FGF_COLS));
+        fg_rhs_fast_kernel<<<grid, 32 * FGF_WARPS, 0, s->stream>>>(
+            s->g, s->u, s->v, s->cflag, s->f, s->gq, s->rhs, (int)row0, (int)row1,
+            make_fg_fast(p.delx, p.dely, p.delt, p.gamma, p.reynolds), 1, with_rhs ? 1 : 0);
+    } else {
+        dim3 grid((unsigned)((row1 - row0 + FGR_ROWS - 1) / FGR_ROWS),
+                  (unsigned)((s->g.NY + FGR_COLS - 1) / FGR_COLS));
+        fg_rhs_kernel<<<grid, 32 * FGR_WARPS, 0, s->stream>>>(
+            s->g, s->u, s->v, s->cflag, s->f, s->gq, s->rhs, row0, row1, s->g.own0,
+            fgr_consts(s), 1, with_rhs ? 1 : 0);
+    }
     s->launches++;
     SB_CUDA(cudaGetLastError());
     return with_rhs ? rhs_halo(s) : SB_OK;
@@ -761,7 +904,8 @@ sb_status launch_rhs(sb_sim *s) {
     int64_t row0 = s->g.own0, row1 = s->g.own1;
     rhs_kernel<<<row_grid(s->g, row1 - row0, s->g.NY), TPB, 0, s->stream>>>(
         s->g, s->f, s->gq, s->rhs, row0, row1, make_divc(s->prm.delx), make_divc(s->prm.dely),
-        make_divc(s->prm.delt));
+        make_divc(s->prm.delt), s->prm.sor_mode == SB_SOR_RED_BLACK ? 1 : 0,
+        make_fg_fast(s->prm.delx, s->prm.dely, s->prm.delt, s->prm.gamma, s->prm.reynolds));
     s->launches++;
     SB_CUDA(cudaGetLastError());
     return rhs_halo(s);
@@ -940,6 +1084,7 @@ void preload_stages() {
     cudaFuncGetAttributes(&a, velocity_bc_gather);
     cudaFuncGetAttributes(&a, velocity_bc_scatter);
     cudaFuncGetAttributes(&a, fg_rhs_kernel);
+    cudaFuncGetAttributes(&a, fg_rhs_fast_kernel);
     cudaFuncGetAttributes(&a, rhs_kernel);
     cudaFuncGetAttributes(&a, pressure_bc_kernel);
     cudaFuncGetAttributes(&a, norm_partial_kernel);

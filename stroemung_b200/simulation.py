@@ -392,5 +392,12 @@ class Simulation:
         return buf[:min(n.value, buf.size)].copy()
 
     @property
+    def last_stage_ms(self):
+        """device ms of the last tick's stages: velocity BC, F/G + RHS, SOR, velocity update"""
+        ms = np.zeros(4)
+        self._check(_capi.lib().sb_last_stage_ms(self._h, _dp(ms)))
+        return ms
+
+    @property
     def last_sor_ms(self):
         return float(_capi.lib().sb_last_sor_ms(self._h))
