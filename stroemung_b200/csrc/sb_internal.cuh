@@ -270,6 +270,7 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h);
 sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h,
                                const RbFin *fin);
 void rb_plan_release(sb_sim *s);
+int rb_stream_slots_per_item(int T);   // partial-sum slots of one streaming work item
 sb_status launch_frozen_mirror(sb_sim *s, int BX, int BY);   // frozen tiles: p[other] := p[cur]
 sb_status launch_frozen_fill(sb_sim *s, int part_stride, int slot);
 void preload_sor_rb_stream();

@@ -648,7 +648,8 @@ sb_status launch_sor_rb_pass(sb_sim *s, int *nparts_out, int norm_only, const Rb
         tile_list = s->plan.d_slow;
     }
     const int n_frozen = (!norm_only && s->dbg.rb_stream) ? s->plan.n_frozen : 0;
-    const int nparts = n_tile + n_items + (n_frozen ? 1 : 0);
+    // partial-sum slots: one per tile, one per warp of a streaming work item, one for the frozen tiles
+    const int nparts = n_tile + n_items * rb_stream_slots_per_item(T) + (n_frozen ? 1 : 0);
     size_t need = (size_t)nparts * TMAX + 64;
     if (need > s->partial_cap) {  // stream-ordered: no device-wide synchronisation
         if (s->d_partial) SB_CUDA(cudaFreeAsync(s->d_partial, s->stream));

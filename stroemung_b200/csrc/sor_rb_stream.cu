@@ -71,8 +71,8 @@ constexpr int TC_NEED_NEXT = 32;
 
 // Everything that indexes a ring is a compile-time constant inside the unrolled window:
 //   * the tick loop is unrolled over NW = 2T+4 ticks (the register window), U = tick mod NW;
-//   * row R lands in slot U of the rhs ring (NW slots, one mbarrier each) and in slot
-//     U mod (T+2) of the p ring (NW/2 slots: a p row is consumed in its arrival tick);
+//   * row R lands in slot U of the rhs ring (one mbarrier per slot) and in slot U mod (T+2)
+//     of the p ring (a p row is consumed in its arrival tick);
 //   * the rhs of row q is read at ticks q+1, q+3, .. q+2T-1 (the red half-sweeps; the black
 //     cells' values are carried one tick in registers) -- the red values read at q+2T-1 are
 //     carried two more ticks for the residual of the last sweep, so a slot is free 2T ticks
@@ -86,31 +86,49 @@ __host__ __device__ constexpr int stream_np(int T) { return T + 2; }
 __host__ __device__ constexpr int stream_pf(int T) {
     return SB_STREAM_PF < T + 1 ? SB_STREAM_PF : T + 1;
 }
-// shared memory of one warp (rings + mbarriers), padded to the 128-byte ring alignment
-__host__ __device__ constexpr int stream_smem(int TB) {
-    return ((stream_np(TB) + stream_nw(TB)) * ROW_BYTES + stream_nw(TB) * 8 + 127) / 128 * 128;
-}
-// warps per SM the register budget of the TB instantiation is cut for.  The register file
-// is split per SM sub-partition (16 K registers each), so the steps are 16 warps (128
-// registers per thread), 12 (168) and 8 (255): TB = 4 keeps 48 pressures per lane in flight
-// and needs the last one.
-__host__ __device__ constexpr int stream_warps(int TB) {
-    return TB == 1 ? 16 : TB <= 3 ? 12 : 8;
-}
-// All warps of an SM form ONE CTA (they never synchronise with each other) whose items are
-// all of the same kind (plain / wall strip), so an SM runs one copy of the unrolled window:
-// it is 32 KB (T = 3) to 50 KB (T = 4) of code against 32 KB of L1.5 instruction cache.
-// Against one-warp CTAs this alone gains 8 % at T = 4 (profiles/r1_stream_kinds_ab.txt).
 
-// SB_STREAM_TRACE=1: per item of the last pass: start, end (globaltimer ns), SM, kind
-__device__ unsigned long long g_trace[4096 * 4];
-__device__ unsigned long long g_trace2[4096 * 2];  // first entry into / last exit from the steady loop
-__device__ int g_trace_on;
-__device__ __forceinline__ unsigned long long gtime() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
+// ---- two warps per work item at TB = 4 ("chain") -------------------------------------------
+// A warp that keeps the 2T+4 rows of T = 4 sweeps in registers needs 246 of them (8 warps per
+// SM, two per scheduler) and an unrolled loop of 46 KB against 32 KB of instruction cache; its
+// eight half-sweeps per tick form one dependent chain.  Measured on the B200 (profiles/r2_*):
+// the memory pipeline of the pass alone takes 0.29 ms at 8192^2, the whole pass 0.39 ms, the
+// difference being warps that wait on their own arithmetic (stall samples: no instruction
+// 22 %, fixed-latency wait 22 %).  So at TB = 4 an item is run by TWO warps, each with the
+// window of T = 2:
+//   HEAD  requests the rows (TMA), runs sweeps 0-1 and hands every row it retires to
+//   TAIL  through a 4-row shared-memory ring (two mbarriers per slot: full / empty); TAIL runs
+//         sweeps 2-3, takes the late residuals and stores the row (and a slab's edge rows).
+// TAIL reads its rhs rows from HEAD's rhs ring, which therefore keeps three windows' worth of
+// rows (banks that rotate once per loop iteration; the hand-over ring's back pressure keeps
+// HEAD from overwriting a row TAIL still reads).  Both run the T = 2 code: 20 KB of loop,
+// 164 registers, 12 warps per SM, chains of four half-sweeps -- and the HBM traffic of T = 4.
+constexpr int ROLE_SOLO = 0, ROLE_HEAD = 1, ROLE_TAIL = 2;
+constexpr int CHAIN_TW = 2;        // sweeps per warp of a chain
+constexpr int CHAIN_D = 4;         // rows in the hand-over ring (divides stream_nw(CHAIN_TW))
+constexpr int CHAIN_BANKS = 3;     // rhs ring = 3 windows of HEAD
+__host__ __device__ constexpr bool stream_chained(int TB) { return TB == 4; }
+// warps of a CTA / work items of a CTA.  The register file is split per SM sub-partition
+// (16 K registers each), so the steps are 16 warps (128 registers per thread), 12 (168) and
+// 8 (255)
+__host__ __device__ constexpr int stream_warps(int TB) { return TB == 1 ? 16 : 12; }
+__host__ __device__ constexpr int stream_items_per_cta(int TB) {
+    return stream_chained(TB) ? stream_warps(TB) / 2 : stream_warps(TB);
 }
+// partial-sum slots per item (one per warp that works on it)
+__host__ __device__ constexpr int stream_slots_per_item(int TB) { return stream_chained(TB) ? 2 : 1; }
+// shared memory of one work item (rings + mbarriers), padded to the 128-byte ring alignment.
+//   solo:  p ring T+2 rows, rhs ring 2T+4 rows, 2T+4 mbarriers
+//   chain: p ring, 3 x rhs window, hand-over ring, arrival + full + empty mbarriers; the
+//          shortened passes (T < 4: one warp of the pair runs them alone) fit inside
+__host__ __device__ constexpr int stream_smem(int TB) {
+    return stream_chained(TB)
+               ? ((stream_np(CHAIN_TW) + CHAIN_BANKS * stream_nw(CHAIN_TW) + CHAIN_D) * ROW_BYTES +
+                  (stream_nw(CHAIN_TW) + 2 * CHAIN_D) * 8 + 127) / 128 * 128
+               : ((stream_np(TB) + stream_nw(TB)) * ROW_BYTES + stream_nw(TB) * 8 + 127) / 128 * 128;
+}
+// All warps of an SM form ONE CTA (apart from the pairs of a chain they never synchronise with
+// each other) whose items are all of the same kind (plain / wall strip), so an SM runs one
+// copy of the unrolled window (profiles/r1_stream_kinds_ab.txt: +8 % against one-warp CTAs).
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -130,14 +148,22 @@ struct SCtx {
     int cx0, cx1;              // rows swept and counted (the stored rows minus boundary rows)
     int bc_lo, bc_hi;          // boundary rows of the item (far out of range if none)
     int first, re;             // rows loaded: [first, re)
-    int rend;                  // ticks run for rows [rs, rend): rend = x1 + 2T+2 (drain)
-    int trace_idx;             // SB_STREAM_TRACE: slot of this item, -1 = none
+    int rend;                  // ticks run for rows [rs, rend)
+    int rs, hend;              // chain: rows [rs, hend) go through the hand-over ring, in order
+    int group_bar;             // chain: named barrier of the warp pair
     int lane, lane_m1, lane_p1;
     bool cmA, cmB;             // the pair lies in the strip's stored / counted columns
     bool keepA, keepB;         // A0 / B1 of this lane is a wall cell
-    double *pring, *rring;     // ring bases
-    const double *pl, *rl;     // this lane's pair A in slot 0 of the p / rhs ring
-    uint64_t *bar;
+    double *pring;             // p ring base (HEAD / SOLO)
+    double *rring;             // rhs ring base: bank 0
+    const double *pl;          // this lane's pair A in slot 0 of the p ring
+    // this lane's pair A in slot 0 of the rhs bank of this loop iteration / the one before;
+    // the bank the requests of this iteration's last PF ticks go to (HEAD / SOLO)
+    const double *rl_cur, *rl_prev;
+    double *rr_cur, *rr_next;
+    uint64_t *bar;             // arrival barriers of the rhs slots of one window
+    double *hring;             // hand-over ring (chain), this lane's pair A in slot 0
+    uint64_t *hfull, *hempty;
     RbConsts k;
 };
 
@@ -153,13 +179,14 @@ struct StreamPeers {
     const SorCtl *ctl;
 };
 
-// request row `row` (both arrays) into rhs slot `slot` / p slot `slot % NP`; lane 0 only
+// request row at offset `off` (both arrays): rhs into slot `slot` of bank `rbank`, p into slot
+// `slot % NP`; lane 0 only
 template <int NP>
-__device__ __forceinline__ void issue_row(const SCtx &c, int64_t off, int slot) {
+__device__ __forceinline__ void issue_row(const SCtx &c, double *rbank, int64_t off, int slot) {
     uint64_t *bar = c.bar + slot;
     mbar_expect_tx(bar, 2 * ROW_BYTES);
     bulk_load(c.pring + (slot % NP) * SW, c.pin + off, ROW_BYTES, bar);
-    bulk_load(c.rring + slot * SW, c.rhs + off, ROW_BYTES, bar);
+    bulk_load(rbank + slot * SW, c.rhs + off, ROW_BYTES, bar);
 }
 
 // The two cells of one colour in a lane's two column pairs.  SET 0: the first cells A0, B0
@@ -187,15 +214,16 @@ __device__ __forceinline__ double tsum(const RbConsts &k, double xs, double ys, 
     return fma(k.rdx2, xs, fma(k.rdy2, ys, -rh));
 }
 
-// One half-sweep of sweep kk (RED: first colour) on the row in register slot s, cells SET.
+// One half-sweep (RED: first colour) on the row in register slot s, cells SET; g = the sweep's
+// index in the PASS (a TAIL warp starts at g = 2).
 //   RED:   rhs from the ring (the other colour's values are carried to the black half-sweep
-//          of the next tick); the residuals of sweep kk-1 of these cells are taken here, one
-//          sweep late (LATE = kk > 0, into acc*[kk-1]); boundary cells are refreshed.
-//   black: rhs carried; residuals of sweep kk right after the update.
+//          of the next tick); the residuals of sweep g-1 of these cells are taken here, one
+//          sweep late (LATE = g > 0, into acc_*); boundary cells are refreshed.
+//   black: rhs carried; residuals of sweep g right after the update.
 // q = the row; STEADY: q is an ordinary counted row (no row tests).
 template <int T, bool STEADY, int WALL, int SET, bool RED>
 __device__ __forceinline__ void half_sweep(double (&W)[2 * T + 4][4], const int s, const int q,
-                                           const int kk, const double rha, const double rhb,
+                                           const int g, const double rha, const double rhb,
                                            double &acc_a, double &acc_b, const SCtx &c) {
 #ifdef SB_STREAM_NOCOMPUTE   // experiment: the memory pipeline of the pass alone (wrong results)
     return;
@@ -213,7 +241,7 @@ __device__ __forceinline__ void half_sweep(double (&W)[2 * T + 4][4], const int 
     const int sm = (s + NW - 1) % NW, sp = (s + 1) % NW;
     if (!STEADY && (q == c.bc_lo || q == c.bc_hi)) return;   // a boundary row: not swept
     const bool rv = STEADY || (unsigned)(q - c.cx0) < (unsigned)(c.cx1 - c.cx0);
-    const bool late = RED && kk > 0;
+    const bool late = RED && g > 0;
     // boundary refresh of this iteration (red half-sweep only): wall cell <- its fluid
     // neighbour; boundary row <- this row (corner cells on the wall column keep their value)
     const bool row_lo = !STEADY && RED && q == c.bc_lo + 1;
@@ -247,14 +275,14 @@ __device__ __forceinline__ void half_sweep(double (&W)[2 * T + 4][4], const int 
     double xa = W[sp][ia] + W[sm][ia], xb = W[sp][ib] + W[sm][ib];
     double ta = tsum(k, xa, W[s][oa] + na, rha), tb = tsum(k, xb, W[s][ob] + nb, rhb);
     if (late) {
-        if (rv) {  // residuals of sweep kk-1 with the boundary values of sweep kk-1
+        if (rv) {  // residuals of sweep g-1 with the boundary values of sweep g-1
             double ra = fma(-k.diag, W[s][ia], ta), rb = fma(-k.diag, W[s][ib], tb);
             if (wall_a) ra = c.keepA ? 0.0 : ra;
             if (wall_b) rb = c.keepB ? 0.0 : rb;
             acc_a = fma(ra, ra, acc_a);
             acc_b = fma(rb, rb, acc_b);
         }
-        if (adj_a || adj_b) {  // now the wall cell moves on to sweep kk: retake the sum
+        if (adj_a || adj_b) {  // now the wall cell moves on to sweep g: retake the sum
             refresh_wall();
             if (adj_a) ta = tsum(k, xa, W[s][oa] + na, rha);
             if (adj_b) tb = tsum(k, xb, W[s][ob] + nb, rhb);
@@ -283,49 +311,73 @@ __device__ __forceinline__ void half_sweep(double (&W)[2 * T + 4][4], const int 
 
 // One tick: row R has been requested PF ticks ago.  U = (R - rs) mod NW is the register slot
 // of row R and its ring slot; after inlining into the unrolled loop every index below is a
-// constant.  roff = R * pitch.  ph = parity of the mbarrier phase of this loop iteration.
-// STEADY: every row this tick touches is an ordinary counted row (no row tests at all).
-template <int T, bool STEADY, int WALL>
+// constant.  roff = R * pitch.  ph = parity of the loop iteration `it`; KB = index in the
+// pass of this warp's first sweep.  acc*[g - AB] collects level g, AB = max(KB - 1, 0).
+// STEADY: every row this tick touches is an ordinary counted row (no row tests at all) and
+// (chain) every hand-over slot has been used before.
+template <int T, bool STEADY, int WALL, int ROLE, int KB>
 __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&C)[T][2],
-                                            double (&FR)[2][2], double (&accA)[T],
-                                            double (&accB)[T], const int U, const int R,
-                                            const int64_t roff, const uint32_t ph,
+                                            double (&FR)[2][2], double (&accA)[T + 1],
+                                            double (&accB)[T + 1], const int U, const int R,
+                                            const int64_t roff, const uint32_t ph, const int it,
                                             const SCtx &c, const StreamPeers &pe) {
     constexpr int NW = stream_nw(T), NP = stream_np(T), PF = stream_pf(T);
+    constexpr int AB = KB > 0 ? KB - 1 : 0;
+    constexpr int D = CHAIN_D;
     const RbConsts &k = c.k;
-    // ---- request row R + PF; row R: shared-memory ring -> registers ------------------------
+    // ---- row R: requested (HEAD / SOLO: row R + PF goes out) or handed over -> registers ------
     __syncwarp();  // every lane is done with the slots the request overwrites
-    if (c.lane == 0) {
-        if (STEADY || R + PF < c.re) issue_row<NP>(c, roff + PF * c.pitch, (U + PF) % NW);
-        if (!STEADY && R < c.first) mbar_arrive(c.bar + U);  // keeps the phases in step
-    }
-    if (STEADY || (R >= c.first && R < c.re)) {
-        mbar_wait(c.bar + U, ph);
-        const double *src = c.pl + (U % NP) * SW;
-        const double2 a = *reinterpret_cast<const double2 *>(src);
-        const double2 b = *reinterpret_cast<const double2 *>(src + 64);
-        W[U][0] = a.x; W[U][1] = a.y; W[U][2] = b.x; W[U][3] = b.y;
+    if constexpr (ROLE != ROLE_TAIL) {
+        if (c.lane == 0) {
+            if (STEADY || R + PF < c.re)
+                issue_row<NP>(c, U + PF < NW ? c.rr_cur : c.rr_next, roff + PF * c.pitch, (U + PF) % NW);
+            if (!STEADY && R < c.first) mbar_arrive(c.bar + U);  // keeps the phases in step
+        }
+        if (STEADY || (R >= c.first && R < c.re)) {
+            mbar_wait(c.bar + U, ph);
+            const double *src = c.pl + (U % NP) * SW;
+            const double2 a = *reinterpret_cast<const double2 *>(src);
+            const double2 b = *reinterpret_cast<const double2 *>(src + 64);
+            W[U][0] = a.x; W[U][1] = a.y; W[U][2] = b.x; W[U][3] = b.y;
+        } else {
+            W[U][0] = W[U][1] = W[U][2] = W[U][3] = 0.0;
+        }
     } else {
-        W[U][0] = W[U][1] = W[U][2] = W[U][3] = 0.0;
+        // every row from rs on takes its turn in the ring (rows before `first` carry zeros),
+        // so that use n of a slot is row rs + n D + slot for both warps
+        if (STEADY || R < c.hend) {
+            // the n-th use of slot U % D, n = it * (NW / D) + U / D: parity (U / D) & 1
+            static_assert((NW / D) % 2 == 0, "static hand-over phases need an even NW / D");
+            mbar_wait(c.hfull + U % D, (uint32_t)((U / D) & 1));
+            const double *src = c.hring + (U % D) * SW;
+            const double2 a = *reinterpret_cast<const double2 *>(src);
+            const double2 b = *reinterpret_cast<const double2 *>(src + 64);
+            W[U][0] = a.x; W[U][1] = a.y; W[U][2] = b.x; W[U][3] = b.y;
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(c.hempty + U % D);
+        } else {
+            W[U][0] = W[U][1] = W[U][2] = W[U][3] = 0.0;
+        }
     }
     double fr_a = 0.0, fr_b = 0.0;  // red rhs of the row of the last red half-sweep
 #pragma unroll
     for (int kk = 0; kk < T; kk++) {
         double carry_a, carry_b;
-        const int lv = kk > 0 ? kk - 1 : 0;  // level of the late red residuals
+        const int g = KB + kk;                      // sweep index in the pass
+        const int lv = (g > 0 ? g - 1 : 0) - AB;    // accumulator of the late red residuals
         {   // ---- red half-sweep of sweep kk on row R - (2kk+1) -----------------------------
             const int lag = 2 * kk + 1;
             const int s = (U + 2 * NW - lag) % NW;
-            const double *rp = c.rl + s * SW;
+            const double *rp = (U >= lag ? c.rl_cur : c.rl_prev) + s * SW;
             const double2 rA = *reinterpret_cast<const double2 *>(rp);
             const double2 rB = *reinterpret_cast<const double2 *>(rp + 64);
             if ((s & 1) == 0) {  // row parity (rs has even global x, NW is even)
-                half_sweep<T, STEADY, WALL, 0, true>(W, s, R - lag, kk, rA.x, rB.x, accA[lv],
+                half_sweep<T, STEADY, WALL, 0, true>(W, s, R - lag, g, rA.x, rB.x, accA[lv],
                                                      accB[lv], c);
                 carry_a = rA.y; carry_b = rB.y;
                 if (kk == T - 1) { fr_a = rA.x; fr_b = rB.x; }
             } else {
-                half_sweep<T, STEADY, WALL, 1, true>(W, s, R - lag, kk, rA.y, rB.y, accA[lv],
+                half_sweep<T, STEADY, WALL, 1, true>(W, s, R - lag, g, rA.y, rB.y, accA[lv],
                                                      accB[lv], c);
                 carry_a = rA.x; carry_b = rB.x;
                 if (kk == T - 1) { fr_a = rA.y; fr_b = rB.y; }
@@ -335,18 +387,19 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
             const int lag = 2 * kk + 2;
             const int s = (U + 2 * NW - lag) % NW;
             if ((s & 1) == 0)  // black cells of an even row: the second cells
-                half_sweep<T, STEADY, WALL, 1, false>(W, s, R - lag, kk, C[kk][0], C[kk][1],
-                                                      accA[kk], accB[kk], c);
+                half_sweep<T, STEADY, WALL, 1, false>(W, s, R - lag, g, C[kk][0], C[kk][1],
+                                                      accA[g - AB], accB[g - AB], c);
             else
-                half_sweep<T, STEADY, WALL, 0, false>(W, s, R - lag, kk, C[kk][0], C[kk][1],
-                                                      accA[kk], accB[kk], c);
+                half_sweep<T, STEADY, WALL, 0, false>(W, s, R - lag, g, C[kk][0], C[kk][1],
+                                                      accA[g - AB], accB[g - AB], c);
         }
         C[kk][0] = carry_a;
         C[kk][1] = carry_b;
     }
-    // ---- residual of the red cells of the last sweep on row R - (2T+1); its red rhs values
-    //      were read two ticks ago (FR[U & 1]); no boundary cell has been refreshed since ------
-    {
+    // ---- residual of the red cells of the LAST sweep of the pass on row R - (2T+1); its red
+    //      rhs values were read two ticks ago (FR[U & 1]); no boundary cell has been refreshed
+    //      since.  (A HEAD warp leaves the late residuals of its last sweep to TAIL.) ----------
+    if constexpr (ROLE != ROLE_HEAD) {
         const int lag = 2 * T + 1;
         const int s = (U + 2 * NW - lag) % NW, sm = (s + NW - 1) % NW, sp = (s + 1) % NW;
         const int q = R - lag;
@@ -371,14 +424,33 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
                          tsum(k, W[sp][3] + W[sm][3], W[s][2] + nb, FR[U & 1][1]));
                 if (WALL) rb = c.keepB ? 0.0 : rb;
             }
-            accA[T - 1] = fma(ra, ra, accA[T - 1]);
-            accB[T - 1] = fma(rb, rb, accB[T - 1]);
+            accA[KB + T - 1 - AB] = fma(ra, ra, accA[KB + T - 1 - AB]);
+            accB[KB + T - 1 - AB] = fma(rb, rb, accB[KB + T - 1 - AB]);
         }
         FR[U & 1][0] = fr_a;
         FR[U & 1][1] = fr_b;
     }
     // ---- retire row R - (2T+2): nothing reads it any more ----------------------------------
-    {
+    if constexpr (ROLE == ROLE_HEAD) {
+        // to TAIL through the hand-over ring: every row that was loaded, in order.  Row q is the
+        // n-th use of slot (q - rs) % D with n = it * (NW / D) + floor((U - lag) / D); the slot is
+        // free once TAIL has read use n - 1
+        constexpr int lag = 2 * T + 2;
+        const int s = (U + 2 * NW - lag) % NW;
+        const int q = R - lag;
+        const int d = U - lag;                                   // in [-lag, NW - 1 - lag]
+        const int hs = ((d % D) + D) % D;
+        const int nrel = (d - hs) / D;                           // floor(d / D)
+        if (STEADY || (q >= c.rs && q < c.hend)) {
+            if (STEADY || it * (NW / D) + nrel >= 1)
+                mbar_wait(c.hempty + hs, (uint32_t)((nrel + 2 * (NW / D) - 1) & 1));
+            double *dst = c.hring + hs * SW;
+            *reinterpret_cast<double2 *>(dst) = make_double2(W[s][0], W[s][1]);
+            *reinterpret_cast<double2 *>(dst + 64) = make_double2(W[s][2], W[s][3]);
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(c.hfull + hs);
+        }
+    } else {
         const int lag = 2 * T + 2;
         const int s = (U + 2 * NW - lag) % NW;
         const int q = R - lag;
@@ -405,96 +477,138 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
     }
 }
 
-template <int T, int WALL>
+// One work item (ROLE_SOLO) or one warp's half of it (chain).  TP = sweeps of the whole pass
+// (levels written); `partial` = this warp's slot of level 0.
+template <int T, int WALL, int ROLE, int KB, int TP>
 __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
                                             double *__restrict__ partial, int64_t part_stride,
                                             const StreamPeers &pe) {
     constexpr int NW = stream_nw(T), NP = stream_np(T), PF = stream_pf(T);
-    constexpr int HP = 2 * T + 2;
+    constexpr int HP = 2 * TP + 2;          // warm-up rows of the whole pass
+    constexpr int AB = KB > 0 ? KB - 1 : 0;
+    constexpr int NBANK = ROLE == ROLE_SOLO ? 1 : CHAIN_BANKS;
     const bool lo = flags & IT_BC_LO, hi = flags & IT_BC_HI;
     c.first = lo ? c.x0 : c.x0 - HP;
     c.re = hi ? c.x1 : c.x1 + HP;
-    c.rend = c.x1 + HP;
+    // the tick loop starts on a row of even global x so that register slot parity = row parity
+    const int rs = c.first - ((gpar + c.first) & 1);
+    c.rs = rs;
+    // TAIL reads rows up to its last tick; HEAD hands over exactly those, the others retire
+    // the stored rows
+    c.hend = min(c.re, c.x1 + 2 * T + 2);
+    c.rend = (ROLE == ROLE_HEAD ? c.hend : c.x1) + 2 * T + 2;
     c.bc_lo = lo ? c.x0 : -(1 << 29);
     c.bc_hi = hi ? c.x1 - 1 : (1 << 29);
     c.cx0 = c.x0 + (lo ? 1 : 0);
     c.cx1 = c.x1 - (hi ? 1 : 0);
     c.keepA = (flags & 3) == IT_WALL_LO && c.lane == 0;
     c.keepB = (flags & 3) == IT_WALL_HI && c.lane == 31;
-    // the tick loop starts on a row of even global x so that register slot parity = row parity
-    const int rs = c.first - ((gpar + c.first) & 1);
     // steady ticks R in [st_lo, st_hi]: rows R-1 .. R-(2T+2) are ordinary counted rows (not
-    // next to a boundary row either) and row R + PF is still to be requested
-    // (a steady tick R retires row R - (2T+2) without tests: not a row a neighbour slab gets)
+    // next to a boundary row either), row R + PF is still to be requested, and a steady tick
+    // retires row R - (2T+2) without tests: not a row a neighbour slab gets.  In a chain the
+    // counted rows of sweep g are the stored rows widened by 2 (TP - 1 - g) on either side,
+    // and every hand-over slot must have been used (two loop iterations in).
     const int lo_end = pe.lo_p[0] != nullptr ? pe.own0 + pe.H : INT_MIN;
     const int hi_beg = pe.hi_p[0] != nullptr ? pe.own1 - pe.H : INT_MAX - 64;
-    const int st_lo = max(c.x0 + (lo ? 2 : 0), lo_end) + 2 * T + 2;
-    const int st_hi = min(min(c.x1 - (hi ? 2 : 0), c.re - PF - 1), hi_beg + 2 * T + 1);
-    if (c.lane == 0) {
+    int st_lo = max(c.x0 + (lo ? 2 : 0), lo_end) + 2 * T + 2;
+    int st_hi = min(min(c.x1 - (hi ? 2 : 0), c.re - PF - 1), hi_beg + 2 * T + 1);
+    if (ROLE != ROLE_SOLO) st_lo = max(st_lo, rs + 2 * NW);
+    if (ROLE == ROLE_TAIL) st_hi = min(c.x1 - (hi ? 2 : 0), hi_beg + 2 * T + 1);
+    if (ROLE != ROLE_TAIL && c.lane == 0) {
         for (int i = 0; i < NW; i++) mbar_init(c.bar + i, 1);
+        if (ROLE == ROLE_HEAD)
+            for (int i = 0; i < CHAIN_D; i++) {
+                mbar_init(c.hfull + i, 1);
+                mbar_init(c.hempty + i, 1);
+            }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // tick R requests row R + PF: rows below rs + PF are requested here
+        // tick R requests row R + PF: rows below rs + PF are requested here (bank 0)
         for (int r = c.first; r < rs + PF; r++)
-            if (r < c.re) issue_row<NP>(c, (int64_t)r * c.pitch, r - rs);
+            if (r < c.re) issue_row<NP>(c, c.rring, (int64_t)r * c.pitch, r - rs);
     }
     __syncwarp();
-    double W[NW][4], C[T][2], FR[2][2], accA[T], accB[T];
+    // TAIL may touch the rings once HEAD has initialised the mbarriers
+    if (ROLE == ROLE_HEAD) asm volatile("bar.arrive %0, 64;" ::"r"(c.group_bar) : "memory");
+    if (ROLE == ROLE_TAIL) asm volatile("bar.sync %0, 64;" ::"r"(c.group_bar) : "memory");
+    double W[NW][4], C[T][2], FR[2][2], accA[T + 1], accB[T + 1];
 #pragma unroll
     for (int i = 0; i < NW; i++) W[i][0] = W[i][1] = W[i][2] = W[i][3] = 0.0;
 #pragma unroll
-    for (int i = 0; i < T; i++) C[i][0] = C[i][1] = accA[i] = accB[i] = 0.0;
+    for (int i = 0; i < T; i++) C[i][0] = C[i][1] = 0.0;
+#pragma unroll
+    for (int i = 0; i <= T; i++) accA[i] = accB[i] = 0.0;
     FR[0][0] = FR[0][1] = FR[1][0] = FR[1][1] = 0.0;
     uint32_t ph = 0;
+    int it = 0, bank = 0;
     int64_t roff = (int64_t)rs * c.pitch;
+    const double *rl0 = c.rring + 2 * c.lane;
+    auto set_banks = [&]() {   // rhs banks of loop iteration `it`: bank = it % NBANK
+        const int prev = bank == 0 ? NBANK - 1 : bank - 1, next = bank == NBANK - 1 ? 0 : bank + 1;
+        c.rl_cur = rl0 + bank * (NW * SW);
+        c.rl_prev = rl0 + prev * (NW * SW);
+        c.rr_cur = c.rring + bank * (NW * SW);
+        c.rr_next = c.rring + next * (NW * SW);
+        bank = next;
+    };
     for (int R0 = rs; R0 < c.rend;) {
+        set_banks();
         if (R0 >= st_lo && R0 + NW - 1 <= st_hi) {
-            if (g_trace_on && c.lane == 0 && c.trace_idx >= 0 && !g_trace2[2 * c.trace_idx])
-                g_trace2[2 * c.trace_idx] = gtime();
             do {  // the steady state: straight-line code, no row tests
 #pragma unroll
                 for (int U = 0; U < NW; U++) {
-                    stream_tick<T, true, WALL>(W, C, FR, accA, accB, U, R0 + U, roff, ph, c, pe);
+                    stream_tick<T, true, WALL, ROLE, KB>(W, C, FR, accA, accB, U, R0 + U, roff, ph, it,
+                                                         c, pe);
                     roff += c.pitch;
                 }
                 ph ^= 1u;
+                it++;
                 R0 += NW;
-            } while (R0 + NW - 1 <= st_hi);
-            if (g_trace_on && c.lane == 0 && c.trace_idx >= 0)
-                g_trace2[2 * c.trace_idx + 1] = gtime();
+                if (R0 + NW - 1 <= st_hi) set_banks();
+                else break;
+            } while (true);
         } else {
 #pragma unroll
             for (int U = 0; U < NW; U++) {
                 if (R0 + U >= c.rend) break;
-                stream_tick<T, false, WALL>(W, C, FR, accA, accB, U, R0 + U, roff, ph, c, pe);
+                stream_tick<T, false, WALL, ROLE, KB>(W, C, FR, accA, accB, U, R0 + U, roff, ph, it, c,
+                                                      pe);
                 roff += c.pitch;
             }
             ph ^= 1u;
+            it++;
             R0 += NW;
         }
     }
+    // this warp's levels: HEAD 0 .. T-1 (the late red residuals of its last sweep are TAIL's),
+    // TAIL KB-1 .. KB+T-1, SOLO 0 .. T-1; every other level of the pass gets a zero
 #pragma unroll
-    for (int i = 0; i < T; i++) {
-        const double v = warp_sum_down((c.cmA ? accA[i] : 0.0) + (c.cmB ? accB[i] : 0.0));
-        if (c.lane == 0) partial[(int64_t)i * part_stride] = v;
+    for (int g = 0; g < TP; g++) {
+        double v = 0.0;
+        if (g >= AB && g - AB <= T && (ROLE == ROLE_TAIL || g < T))
+            v = warp_sum_down((c.cmA ? accA[g - AB] : 0.0) + (c.cmB ? accB[g - AB] : 0.0));
+        if (c.lane == 0) partial[(int64_t)g * part_stride] = v;
     }
 }
 
-template <int T>
+template <int T, int ROLE, int KB, int TP>
 __device__ __forceinline__ void stream_item_any(SCtx &c, int flags, int gpar, double *partial,
                                                 int64_t part_stride, const StreamPeers &pe) {
-    if ((flags & 3) == IT_PLAIN) stream_item<T, 0>(c, flags, gpar, partial, part_stride, pe);
-    else stream_item<T, 1>(c, flags, gpar, partial, part_stride, pe);
+    if ((flags & 3) == IT_PLAIN) stream_item<T, 0, ROLE, KB, TP>(c, flags, gpar, partial, part_stride, pe);
+    else stream_item<T, 1, ROLE, KB, TP>(c, flags, gpar, partial, part_stride, pe);
 }
 
-// one work item per warp, stream_warps(TB) warps per CTA, one CTA per SM; TB = the configured
-// temporal block (the lattice and the shared-memory budget follow it), the pass itself runs
-// ctl->active_T <= TB sweeps.  Items with x1 <= x0 pad a CTA to one kind.
+// One CTA per SM, all its items of one kind.  TB = the configured temporal block (the lattice
+// and the shared-memory budget follow it), the pass itself runs ctl->active_T <= TB sweeps.
+// TB <= 3: one warp per item; TB = 4: two (HEAD / TAIL), and a shortened pass (T < 4) is run
+// by the first warp of each pair alone.  Items with x1 <= x0 pad a CTA to one kind.
 template <int TB>
 __global__ void __launch_bounds__(32 * stream_warps(TB), 1)
 sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict__ pbuf,
                      const double *__restrict__ rhs, SorCtl *ctl, double *partial, int part_base,
                      int part_stride, int64_t pitch, int gpar, RbConsts k, RbFin fin,
                      const __grid_constant__ StreamPeers pe) {
+    constexpr bool CH = stream_chained(TB);
+    constexpr int IPC = stream_items_per_cta(TB), SPI = stream_slots_per_item(TB);
     const int T = ctl->active_T;
     if (T == 0) return;
     const int src = ctl->src;
@@ -502,51 +616,64 @@ sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict
     // broadcast from lane 0: tells the compiler the warp index (and all that follows from
     // it: ring addresses, item fields) is warp-uniform, so it stays on the uniform datapath
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    const int idx = blockIdx.x * stream_warps(TB) + warp;
+    const int slot = CH ? warp >> 1 : warp;          // item of this CTA
+    const int role = CH ? warp & 1 : 0;              // chain: 0 HEAD, 1 TAIL
+    const int idx = blockIdx.x * IPC + slot;
     const RbItem it = items[idx];
     const int flags = it.pad & 0xff, st0 = (it.pad >> 8) & 0xff, st1 = (it.pad >> 16) & 0xff;
     SCtx c;
     c.lane = threadIdx.x & 31;
-    double *part = partial + part_base + idx;
+    double *part = partial + part_base + idx * SPI + role;
     if (it.x1 <= it.x0) {  // padding: contributes nothing
         if (c.lane == 0)
             for (int i = 0; i < T; i++) part[(int64_t)i * part_stride] = 0.0;
     } else {
-    c.lane_m1 = (c.lane + 31) & 31;
-    c.lane_p1 = (c.lane + 1) & 31;
-    // rings of the T actually run: p ring, rhs ring, one mbarrier per rhs slot
-    c.pring = reinterpret_cast<double *>(smem_raw + warp * stream_smem(TB));
-    c.rring = c.pring + stream_np(T) * SW;
-    c.bar = reinterpret_cast<uint64_t *>(c.rring + stream_nw(T) * SW);
-    c.pl = c.pring + 2 * c.lane;
-    c.rl = c.rring + 2 * c.lane;
-    c.pin = pbuf[src] + it.ty0;
-    c.pout = pbuf[src ^ 1] + it.ty0 + 2 * c.lane;
-    c.rhs = rhs + it.ty0;
-    c.pitch = pitch;
-    c.x0 = it.x0;
-    c.x1 = it.x1;
-    c.k = k;
-
-    // stored = counted columns [st0, st1) of the strip (pair-aligned; a wall cell inside is
-    // stored but not counted: keepA / keepB)
-    c.cmA = 2 * c.lane >= st0 && 2 * c.lane < st1;
-    c.cmB = 64 + 2 * c.lane >= st0 && 64 + 2 * c.lane < st1;
-    const bool trace = g_trace_on && idx < 4096;
-    c.trace_idx = trace ? idx : -1;
-    if (trace && c.lane == 0) {
-        g_trace2[2 * idx] = 0;
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        g_trace[4 * idx] = gtime();
-        g_trace[4 * idx + 2] = smid;
-        g_trace[4 * idx + 3] = (unsigned)flags | ((unsigned long long)(it.x1 - it.x0) << 8);
-    }
-    if (T == TB) stream_item_any<TB>(c, flags, gpar, part, part_stride, pe);
-    else if (TB > 1 && T == 1) stream_item_any<1>(c, flags, gpar, part, part_stride, pe);
-    else if (TB > 2 && T == 2) stream_item_any<2>(c, flags, gpar, part, part_stride, pe);
-    else if (TB > 3 && T == 3) stream_item_any<3>(c, flags, gpar, part, part_stride, pe);
-    if (trace && c.lane == 0) g_trace[4 * idx + 1] = gtime();
+        c.lane_m1 = (c.lane + 31) & 31;
+        c.lane_p1 = (c.lane + 1) & 31;
+        unsigned char *base = smem_raw + slot * stream_smem(TB);
+        const bool chain_now = CH && T == TB;
+        // rings of the T actually run: p ring, rhs ring (x 3 banks in a chain), hand-over ring,
+        // then the mbarriers
+        const int tw = chain_now ? CHAIN_TW : T;
+        c.pring = reinterpret_cast<double *>(base);
+        c.rring = c.pring + stream_np(tw) * SW;
+        c.hring = c.rring + (chain_now ? CHAIN_BANKS : 1) * stream_nw(tw) * SW;
+        c.bar = reinterpret_cast<uint64_t *>(c.hring + (chain_now ? CHAIN_D : 0) * SW);
+        c.hfull = c.bar + stream_nw(tw);
+        c.hempty = c.hfull + CHAIN_D;
+        c.hring += 2 * c.lane;
+        c.pl = c.pring + 2 * c.lane;
+        c.pin = pbuf[src] + it.ty0;
+        c.pout = pbuf[src ^ 1] + it.ty0 + 2 * c.lane;
+        c.rhs = rhs + it.ty0;
+        c.pitch = pitch;
+        c.x0 = it.x0;
+        c.x1 = it.x1;
+        c.k = k;
+        c.group_bar = 1 + slot;
+        // stored = counted columns [st0, st1) of the strip (pair-aligned; a wall cell inside is
+        // stored but not counted: keepA / keepB)
+        c.cmA = 2 * c.lane >= st0 && 2 * c.lane < st1;
+        c.cmB = 64 + 2 * c.lane >= st0 && 64 + 2 * c.lane < st1;
+        if (CH) {
+            if (T == TB) {
+                if (role == 0) {
+                    stream_item_any<CHAIN_TW, ROLE_HEAD, 0, TB>(c, flags, gpar, part, part_stride, pe);
+                } else {
+                    stream_item_any<CHAIN_TW, ROLE_TAIL, CHAIN_TW, TB>(c, flags, gpar, part, part_stride, pe);
+                }
+            } else if (role == 0) {
+                if (T == 1) stream_item_any<1, ROLE_SOLO, 0, 1>(c, flags, gpar, part, part_stride, pe);
+                else if (T == 2) stream_item_any<2, ROLE_SOLO, 0, 2>(c, flags, gpar, part, part_stride, pe);
+                else stream_item_any<3, ROLE_SOLO, 0, 3>(c, flags, gpar, part, part_stride, pe);
+            } else if (c.lane == 0) {
+                for (int i = 0; i < T; i++) part[(int64_t)i * part_stride] = 0.0;
+            }
+        } else {
+            if (T == TB) stream_item_any<TB, ROLE_SOLO, 0, TB>(c, flags, gpar, part, part_stride, pe);
+            else if (TB > 1 && T == 1) stream_item_any<1, ROLE_SOLO, 0, 1>(c, flags, gpar, part, part_stride, pe);
+            else if (TB > 2 && T == 2) stream_item_any<2, ROLE_SOLO, 0, 2>(c, flags, gpar, part, part_stride, pe);
+        }
     }
     // ---- the last CTA to finish totals the partials of the whole pass (tile kernel's
     //      included: it ran before), applies the exit rule and advances the control block --
@@ -599,13 +726,22 @@ int stream_cta_warps(int TB) {
     default: return stream_warps(4);
     }
 }
+// work items of one CTA
+int stream_cta_items(int TB) {
+    switch (TB) {
+    case 1: return stream_items_per_cta(1);
+    case 2: return stream_items_per_cta(2);
+    case 3: return stream_items_per_cta(3);
+    default: return stream_items_per_cta(4);
+    }
+}
 // dynamic shared memory of one CTA
 int stream_smem_bytes(int TB) {
     switch (TB) {
-    case 1: return stream_smem(1) * stream_warps(1);
-    case 2: return stream_smem(2) * stream_warps(2);
-    case 3: return stream_smem(3) * stream_warps(3);
-    default: return stream_smem(4) * stream_warps(4);
+    case 1: return stream_smem(1) * stream_items_per_cta(1);
+    case 2: return stream_smem(2) * stream_items_per_cta(2);
+    case 3: return stream_smem(3) * stream_items_per_cta(3);
+    default: return stream_smem(4) * stream_items_per_cta(4);
     }
 }
 
@@ -711,28 +847,9 @@ __global__ void frozen_fill_kernel(const double *__restrict__ part, int n, doubl
 
 }  // namespace
 
-static void dump_trace(sb_sim *s) {
-    std::vector<unsigned long long> t(4096 * 4), t2(4096 * 2);
-    cudaStreamSynchronize(s->stream);
-    if (cudaMemcpyFromSymbol(t.data(), g_trace, t.size() * 8) != cudaSuccess) return;
-    if (cudaMemcpyFromSymbol(t2.data(), g_trace2, t2.size() * 8) != cudaSuccess) return;
-    unsigned long long t0 = ~0ull;
-    const int n = std::min(s->plan.n_items, 4096);
-    for (int i = 0; i < n; i++)
-        if (t[4 * i + 1]) t0 = std::min(t0, t[4 * i]);
-    for (int i = 0; i < n; i++) {
-        if (!t[4 * i + 1]) continue;
-        fprintf(stderr, "[sb trace] rank %d item %d kind %d flags %d rows %d sm %d start %.1f us dur %.1f us"
-                " warmup %.1f steady %.1f drain %.1f\n",
-                s->slab ? s->link.rank : 0, i, (int)(t[4 * i + 3] & 3), (int)(t[4 * i + 3] & 0xff), (int)(t[4 * i + 3] >> 8),
-                (int)t[4 * i + 2], (t[4 * i] - t0) * 1e-3, (t[4 * i + 1] - t[4 * i]) * 1e-3,
-                (t2[2 * i] - t[4 * i]) * 1e-3, (t2[2 * i + 1] - t2[2 * i]) * 1e-3,
-                (t[4 * i + 1] - t2[2 * i + 1]) * 1e-3);
-    }
-}
+int rb_stream_slots_per_item(int T) { return T >= 4 ? stream_slots_per_item(4) : 1; }
 
 void rb_plan_release(sb_sim *s) {
-    if (s->dbg.trace_stream && s->plan.n_items) dump_trace(s);
     cudaFree(s->plan.d_slow);
     cudaFree(s->plan.d_items);
     cudaFree(s->plan.d_plain);
@@ -835,8 +952,8 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
         if (!cls[(size_t)t]) slow.push_back(t);
     // Tiles per item: as many items as fill the SMs in whole waves of CTAs, as long as
     // possible otherwise (every open end of an item pays 2T+2 warm-up rows).  A CTA holds
-    // `nwarp` items of ONE kind.
-    const int nwarp = stream_cta_warps(T);
+    // `nwarp` items of ONE kind (at T = 4 two warps run an item).
+    const int nwarp = stream_cta_items(T);
     {
         // per device: the attributes live with the function in each context
         static bool attrs_set[64] = {false};
@@ -854,7 +971,7 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
     }
     int dev_sms = 148, ctas = 1;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, s->device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, stream_kernel(T), 32 * nwarp,
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, stream_kernel(T), 32 * stream_cta_warps(T),
                                                   stream_smem_bytes(T));
     if (ctas < 1) ctas = 1;
     const int64_t resident = (int64_t)dev_sms * ctas;  // CTAs at a time
@@ -1046,7 +1163,7 @@ sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h,
     const Geom &g = s->g;
     const int gpar = (int)(((g.gx0 % 2) + 2) % 2);
     const int TB = s->prm.temporal_block;
-    const int nw = stream_cta_warps(TB);
+    const int nw = stream_cta_warps(TB), ipc = stream_cta_items(TB);
     RbFin fin{};
     if (fin_in) {
         fin = *fin_in;
@@ -1065,13 +1182,7 @@ sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h,
     }
     pe.pbuf = rb_pbuf_ptr(s);
     pe.ctl = s->d_ctl;
-    static int trace_set = 0;
-    if (!trace_set && s->dbg.trace_stream) {
-        const int one = 1;
-        cudaMemcpyToSymbol(g_trace_on, &one, sizeof(int));
-        trace_set = 1;
-    }
-    stream_kernel(TB)<<<s->plan.n_items / nw, 32 * nw, stream_smem_bytes(TB), s->stream>>>(
+    stream_kernel(TB)<<<s->plan.n_items / ipc, 32 * nw, stream_smem_bytes(TB), s->stream>>>(
         s->plan.d_items, rb_pbuf_ptr(s), s->rhs, s->d_ctl, s->d_partial, part_base, part_stride,
         g.pitch, gpar, rb_consts(s), fin, pe);
     s->launches++;

@@ -83,8 +83,8 @@ def big_case(name):
     elif name == "step-4096x1024":            # C4 in small: solid block with frozen tiles
         size = (4096, 1024)
         g = presets.backward_step(size, size[0] // 4, size[1] // 2)
-    elif name == "wide-260x65536":            # more strips than one wave of work items holds
-        size = (260, 65536)
+    elif name.startswith("wide-260x"):        # more strips than one wave of work items holds
+        size = (260, int(name[len("wide-260x"):]))
         g = presets.simple_inflow(size)
     else:
         raise KeyError(name)
@@ -117,14 +117,16 @@ def test_pass_kernels_at_scale(case, T):
 
 @pytest.mark.parametrize("T", [2, 4])
 def test_several_waves_of_work_items(T):
-    """65536 columns are ~600 strips: more work items than the resident warps hold, so the
-    plan runs several waves of CTAs (the 16384^2 and 32768-wide shapes of config 5)."""
-    unf = big_case("wide-260x65536")
-    ref = oracle_run(("wide-260x65536", T), unf, 2 * T + 1, 1)
+    """65536 columns are ~600 strips, 131072 ~1200: at T = 4 (6 work items per SM, two warps
+    each) more work items than the resident warps hold, so the plan runs several waves of CTAs
+    (the 16384^2 and 32768-wide shapes of config 5)."""
+    name = "wide-260x131072" if T == 4 else "wide-260x65536"
+    unf = big_case(name)
+    ref = oracle_run((name, T), unf, 2 * T + 1, 1)
     sim = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK, temporal_block=T)
     check_against_oracle(sim, ref, 2 * T + 1, 1)
     slow, items = sim.rb_plan
-    resident = 148 * (8 if T == 4 else 12)   # work items (warps) resident at a time
+    resident = 148 * (6 if T == 4 else 12)   # work items resident at a time
     assert slow == 0 and items >= resident, (slow, items, resident)
     if T == 4:
         assert items > resident, (items, resident)   # more than one wave of CTAs
