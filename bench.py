@@ -419,28 +419,81 @@ def run_ours(args):
     total_sweeps = sum(sweeps)
 
     # -- end-to-end: host buffers in, host buffers out, every step --------------------------
+    # Every step uploads p, u, v from pinned host memory, ticks, downloads p, u, v.  N = 1:
+    # through stroemung_b200.pipeline.HostPipeline -- `depth` handles of this geometry, each
+    # with its own stream and host thread calling sb_tick_host, so the upload of one request
+    # overlaps the kernels of another and the download of a third (PCIe is full duplex); the
+    # requests are `depth` independent simulations, each stepped `e2e_steps` times in series
+    # (a step's input is the previous output of the same request).  N > 1: one slab handle per
+    # rank, upload -> halo sync -> tick -> download in series.
     rows = sim._local_shape[0]
     nbytes = rows * ny * 8
-    host = [C.c_void_p(L.sb_host_alloc(nbytes)) for _ in range(3)]
     fields = (_capi.FIELD_P, _capi.FIELD_U, _capi.FIELD_V)
-    for hbuf, fld in zip(host, fields):
-        sim._check(L.sb_download(sim._h, fld, hbuf))
-    e2e_steps = max(1, min(args.steps, 3))
-    barrier()
-    sim.timer_begin()
-    for _ in range(e2e_steps):
+    sim_bytes = rows * ny * 57
+    depth = 1 if world > 1 or args.e2e_depth == 1 or 3 * sim_bytes > 60e9 else args.e2e_depth
+    if depth > 1:
+        import threading
+        import time
+
+        from stroemung_b200.pipeline import HostPipeline
+        first = [sim]
+
+        def make_sim():
+            if first:
+                return first.pop()
+            return multi.from_preset(group, wl["preset"], wl["size"], wl["cell_size"],
+                                     wl["delt"], wl["gamma"], wl["reynolds"], wl["eps"],
+                                     wl["max_iterations"], wl["omega"],
+                                     preset_args=wl["preset_args"], **ext)
+        pipe = HostPipeline(make_sim, depth=depth)
+        req = [[pipe.alloc() for _ in range(3)] for _ in range(depth)]
+        for bufs in req:
+            for hbuf, fld in zip(bufs, fields):
+                sim._check(L.sb_download(sim._h, fld, hbuf))
+        e2e_steps = max(2, min(args.steps, 4))
+        for bufs in req:                      # one untimed step per request (first-touch)
+            pipe.submit(*bufs).result()
+
+        def drive(bufs):
+            for _ in range(e2e_steps):
+                pipe.submit(*bufs).result()   # H2D x3, tick, D2H x3 inside sb_tick_host
+        drivers = [threading.Thread(target=drive, args=(bufs,)) for bufs in req]
+        t0 = time.perf_counter()
+        for t in drivers:
+            t.start()
+        for t in drivers:
+            t.join()                          # every result() has synchronised its stream
+        dt_e2e = time.perf_counter() - t0
+        e2e_total = depth * e2e_steps
+        extra_sims = [s_ for s_ in pipe.sims if s_ is not sim]
+        pipe.sims = []                        # `sim` is closed below, the others here
+        pipe.close()
+        for s_ in extra_sims:
+            s_.close()
+        e2e_how = (f"{depth} requests in flight (HostPipeline: {depth} handles, streams and host "
+                   f"threads, sb_tick_host), {e2e_steps} steps each; host clock around all of them")
+    else:
+        host = [C.c_void_p(L.sb_host_alloc(nbytes)) for _ in range(3)]
         for hbuf, fld in zip(host, fields):
-            sim._check(L.sb_upload(sim._h, fld, hbuf))      # H2D from pinned host memory
-        if world > 1:
-            sim.slab_sync_halos()                           # uploaded rows -> neighbours' halos
-        sim.run_simulation_tick()
-        for hbuf, fld in zip(host, fields):
-            sim._check(L.sb_download(sim._h, fld, hbuf))    # D2H of the step's result
-    dt_e2e = max_over_ranks(sim.timer_end() * 1e-3)
-    barrier()
-    for hbuf in host:
-        L.sb_host_free(hbuf)
-    e2e_value = cells * e2e_steps / dt_e2e / 1e6
+            sim._check(L.sb_download(sim._h, fld, hbuf))
+        e2e_steps = max(1, min(args.steps, 3))
+        barrier()
+        sim.timer_begin()
+        for _ in range(e2e_steps):
+            for hbuf, fld in zip(host, fields):
+                sim._check(L.sb_upload(sim._h, fld, hbuf))      # H2D from pinned host memory
+            if world > 1:
+                sim.slab_sync_halos()                           # uploaded rows -> neighbours' halos
+            sim.run_simulation_tick()
+            for hbuf, fld in zip(host, fields):
+                sim._check(L.sb_download(sim._h, fld, hbuf))    # D2H of the step's result
+        dt_e2e = max_over_ranks(sim.timer_end() * 1e-3)
+        barrier()
+        for hbuf in host:
+            L.sb_host_free(hbuf)
+        e2e_total = e2e_steps
+        e2e_how = "one handle per rank: upload, tick, download in series; CUDA events, max over ranks"
+    e2e_value = cells * e2e_total / dt_e2e / 1e6
 
     # -- roofline of the dominant kernel (the SOR pass) -------------------------------------
     peak, peak_src = measured_peak_gbs()
@@ -537,7 +590,8 @@ def run_ours(args):
                                            (kfix + SOR_BYTES_PER_CELL_SWEEP * k_avg) / 1e6)},
         "roofline": roof, "cpu_baseline": cpu, "verify": verify, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * nbytes * n_gpus,
-                "d2h_bytes_per_step": 3 * nbytes * n_gpus, "steps": e2e_steps},
+                "d2h_bytes_per_step": 3 * nbytes * n_gpus, "steps": e2e_total,
+                "in_flight": depth, "how": e2e_how},
         "gpu_launches": launches,
     }
     print(json.dumps(line))
@@ -556,6 +610,8 @@ def main():
     ap.add_argument("--size", type=int, nargs=2, default=None)
     ap.add_argument("--mode", default="rb", choices=["rb", "lex"])
     ap.add_argument("--tblock", type=int, default=0)
+    ap.add_argument("--e2e-depth", type=int, default=3,
+                    help="requests in flight in the end-to-end leg at N = 1 (1 = serial)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()

@@ -139,6 +139,18 @@ sb_status sb_tick(sb_sim *sim, uint32_t *sor_iterations, double *norm_squared);
  * the tick 20x per frame, src/lib.rs:214-219); returns the last tick's pair */
 sb_status sb_run_ticks(sb_sim *sim, uint32_t n, uint32_t *sor_iterations, double *norm_squared);
 
+/* One tick on HOST buffers: the call a host-side owner of the fields makes (the reference
+ * keeps `pressure`, `u`, `v` in host arrays, src/grid/mod.rs:112-125, and ticks them in
+ * place, src/simulation.rs:324-333).  Uploads p, u, v ([rows][ny] f64, this slab's own rows),
+ * runs sb_tick, downloads the three fields into p_out, u_out, v_out (may alias the inputs);
+ * all copies are asynchronous on the handle's stream with ONE synchronisation at the end, so
+ * several handles driven from several host threads overlap their copies (PCIe is full
+ * duplex) and their kernels (stroemung_b200/pipeline.py).  Page-locked buffers
+ * (sb_host_alloc) make the copies truly asynchronous. */
+sb_status sb_tick_host(sb_sim *sim, const double *p_in, const double *u_in, const double *v_in,
+                       double *p_out, double *u_out, double *v_out, uint32_t *sor_iterations,
+                       double *norm_squared);
+
 /* stage entry points, one per reference function (stage-level parity) */
 sb_status sb_set_boundary_u_and_v(sb_sim *sim);        /* src/grid/mod.rs:414-651   */
 sb_status sb_calculate_f_and_g(sb_sim *sim);           /* src/simulation.rs:122-202 */

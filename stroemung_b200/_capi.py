@@ -61,7 +61,7 @@ class State(C.Structure):
 
 # every symbol include/stroemung_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "sb_create", "sb_destroy", "sb_tick", "sb_run_ticks", "sb_set_boundary_u_and_v",
+    "sb_create", "sb_destroy", "sb_tick", "sb_tick_host", "sb_run_ticks", "sb_set_boundary_u_and_v",
     "sb_calculate_f_and_g", "sb_calculate_rhs", "sb_copy_pressure_to_boundaries",
     "sb_calculate_norm_squared", "sb_solve_sor", "sb_set_u_and_v",
     "sb_calculate_pressure_range", "sb_calculate_speed_range", "sb_sor_sweeps", "sb_download",
@@ -98,6 +98,7 @@ def lib():
                              C.c_int),
         "sb_destroy": ([vp], None),
         "sb_tick": ([vp, u32p, dp], C.c_int),
+        "sb_tick_host": ([vp, vp, vp, vp, vp, vp, vp, u32p, dp], C.c_int),
         "sb_run_ticks": ([vp, C.c_uint32, u32p, dp], C.c_int),
         "sb_calculate_norm_squared": ([vp, dp], C.c_int),
         "sb_solve_sor": ([vp, u32p, dp], C.c_int),

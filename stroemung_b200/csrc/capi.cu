@@ -580,6 +580,35 @@ sb_status sb_tick(sb_sim *sim, uint32_t *sor_iterations, double *norm_squared) {
     return SB_OK;
 }
 
+static double *field_ptr(sb_sim *s, sb_field f);
+
+sb_status sb_tick_host(sb_sim *sim, const double *p_in, const double *u_in, const double *v_in,
+                       double *p_out, double *u_out, double *v_out, uint32_t *sor_iterations,
+                       double *norm_squared) {
+    SB_ENTER(sim);
+    if (!p_in || !u_in || !v_in || !p_out || !u_out || !v_out) return SB_INVALID_ARGUMENT;
+    if (sim->slab) {
+        set_error("sb_tick_host: row slabs upload with sb_upload + sb_slab_sync_halos");
+        return SB_INVALID_ARGUMENT;
+    }
+    sb_status st;
+    const double *in[3] = {p_in, u_in, v_in};
+    double *out[3] = {p_out, u_out, v_out};
+    const sb_field fld[3] = {SB_FIELD_P, SB_FIELD_U, SB_FIELD_V};
+    sim->uvmax_valid = false;
+    for (int i = 0; i < 3; i++)
+        if ((st = copy_rows_h2d(sim, field_ptr(sim, fld[i]), in[i], 8))) return st;
+    uint32_t it = 0;
+    double n = 0.0;
+    if ((st = tick(sim, &it, &n))) return st;
+    for (int i = 0; i < 3; i++)   // field_ptr again: the tick may have swapped the p buffers
+        if ((st = copy_rows_d2h(sim, out[i], field_ptr(sim, fld[i]), 8))) return st;
+    SB_CUDA(cudaStreamSynchronize(sim->stream));
+    if (sor_iterations) *sor_iterations = it;
+    if (norm_squared) *norm_squared = n;
+    return SB_OK;
+}
+
 sb_status sb_run_ticks(sb_sim *sim, uint32_t n, uint32_t *sor_iterations, double *norm_squared) {
     SB_ENTER(sim);
     uint32_t it = 0;

@@ -311,6 +311,23 @@ class Simulation:
         self._check(_capi.lib().sb_tick(self._h, C.byref(it), C.byref(nrm)))
         return it.value, nrm.value
 
+    def tick_host(self, p_in, u_in, v_in, p_out=None, u_out=None, v_out=None):
+        """One tick on HOST buffers (sb_tick_host): upload p, u, v, tick, download them, one
+        synchronisation.  Buffers are addresses (int / c_void_p, e.g. from sb_host_alloc) or
+        C-contiguous float64 arrays of this handle's shape; outputs default to the inputs
+        (in place, like the reference's tick on its own arrays)."""
+        def addr(b):
+            if isinstance(b, np.ndarray):
+                assert b.dtype == np.float64 and b.flags.c_contiguous and b.shape == self._local_shape
+                return C.c_void_p(b.ctypes.data)
+            return b if isinstance(b, C.c_void_p) else C.c_void_p(b)
+        outs = [i if o is None else o for i, o in zip((p_in, u_in, v_in), (p_out, u_out, v_out))]
+        it, nrm = C.c_uint32(), C.c_double()
+        self._check(_capi.lib().sb_tick_host(self._h, addr(p_in), addr(u_in), addr(v_in),
+                                             addr(outs[0]), addr(outs[1]), addr(outs[2]),
+                                             C.byref(it), C.byref(nrm)))
+        return it.value, nrm.value
+
     def run_ticks(self, n):
         it, nrm = C.c_uint32(), C.c_double()
         self._check(_capi.lib().sb_run_ticks(self._h, n, C.byref(it), C.byref(nrm)))
