@@ -130,6 +130,11 @@ __host__ __device__ constexpr int stream_smem(int TB) {
 // each other) whose items are all of the same kind (plain / wall strip), so an SM runs one
 // copy of the unrolled window (profiles/r1_stream_kinds_ab.txt: +8 % against one-warp CTAs).
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -328,10 +333,15 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
     // ---- row R: requested (HEAD / SOLO: row R + PF goes out) or handed over -> registers ------
     __syncwarp();  // every lane is done with the slots the request overwrites
     if constexpr (ROLE != ROLE_TAIL) {
-        if (c.lane == 0) {
-            if (STEADY || R + PF < c.re)
+        if (STEADY) {
+            // the warp is converged here: elect.sync lets the copies issue from straight-line
+            // code (a `lane == 0` branch makes ptxas wrap each UBLKCP in an election loop)
+            if (elect_one())
                 issue_row<NP>(c, U + PF < NW ? c.rr_cur : c.rr_next, roff + PF * c.pitch, (U + PF) % NW);
-            if (!STEADY && R < c.first) mbar_arrive(c.bar + U);  // keeps the phases in step
+        } else if (c.lane == 0) {
+            if (R + PF < c.re)
+                issue_row<NP>(c, U + PF < NW ? c.rr_cur : c.rr_next, roff + PF * c.pitch, (U + PF) % NW);
+            if (R < c.first) mbar_arrive(c.bar + U);  // keeps the phases in step
         }
         if (STEADY || (R >= c.first && R < c.re)) {
             mbar_wait(c.bar + U, ph);
@@ -616,8 +626,11 @@ sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict
     // broadcast from lane 0: tells the compiler the warp index (and all that follows from
     // it: ring addresses, item fields) is warp-uniform, so it stays on the uniform datapath
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    const int slot = CH ? warp >> 1 : warp;          // item of this CTA
-    const int role = CH ? warp & 1 : 0;              // chain: 0 HEAD, 1 TAIL
+    // chain: warps 0 .. IPC-1 are the HEADs, IPC .. 2 IPC-1 the TAILs, so that every scheduler
+    // (warp index mod 4) carries both roles (HEAD is the slower one: -3 % per pass against
+    // HEAD / TAIL on alternating warps, profiles/r2_stream_chain_ab.txt)
+    const int slot = CH ? warp % IPC : warp;         // item of this CTA
+    const int role = CH ? warp / IPC : 0;            // chain: 0 HEAD, 1 TAIL
     const int idx = blockIdx.x * IPC + slot;
     const RbItem it = items[idx];
     const int flags = it.pad & 0xff, st0 = (it.pad >> 8) & 0xff, st1 = (it.pad >> 16) & 0xff;
