@@ -106,11 +106,30 @@ constexpr int ROLE_SOLO = 0, ROLE_HEAD = 1, ROLE_TAIL = 2;
 constexpr int CHAIN_TW = 2;        // sweeps per warp of a chain
 constexpr int CHAIN_D = 4;         // rows in the hand-over ring (divides stream_nw(CHAIN_TW))
 constexpr int CHAIN_BANKS = 3;     // rhs ring = 3 windows of HEAD
+// A chain warp's tick takes TWO rows (stream_tick2): half the ticks, and the two rows of a
+// half-sweep are independent instruction streams inside one warp.  Rows are requested and
+// handed over in aligned pairs (one mbarrier per pair).
+constexpr int CHAIN_NP = stream_nw(CHAIN_TW);   // p ring of a chain's HEAD: pairs stay aligned
+#ifndef SB_CHAIN_PF
+#define SB_CHAIN_PF 4
+#endif
+constexpr int CHAIN_PF = SB_CHAIN_PF;           // rows requested ahead (even)
+static_assert(CHAIN_PF % 2 == 0 && CHAIN_PF + 2 <= CHAIN_NP, "p ring: rows in flight + the arriving pair");
+static_assert(CHAIN_D % 2 == 0 && stream_nw(CHAIN_TW) % CHAIN_D == 0, "hand-over ring of whole pairs");
+// HEAD in tick R requests rows up to R + PF + 1 and may run 2 TW + D + 2 rows ahead of TAIL,
+// which still reads the rhs of row R' - 2 TW + 1 in its tick R'
+static_assert(CHAIN_PF + 2 + 2 * CHAIN_TW + CHAIN_D + 2 + 2 * CHAIN_TW <= CHAIN_BANKS * stream_nw(CHAIN_TW),
+              "rhs ring too short for the chain");
 __host__ __device__ constexpr bool stream_chained(int TB) { return TB == 4; }
 // warps of a CTA / work items of a CTA.  The register file is split per SM sub-partition
 // (16 K registers each), so the steps are 16 warps (128 registers per thread), 12 (168) and
 // 8 (255)
-__host__ __device__ constexpr int stream_warps(int TB) { return TB == 1 ? 16 : 12; }
+#ifndef SB_CHAIN_WARPS
+#define SB_CHAIN_WARPS 12
+#endif
+__host__ __device__ constexpr int stream_warps(int TB) {
+    return TB == 1 ? 16 : TB == 4 ? SB_CHAIN_WARPS : 12;
+}
 __host__ __device__ constexpr int stream_items_per_cta(int TB) {
     return stream_chained(TB) ? stream_warps(TB) / 2 : stream_warps(TB);
 }
@@ -122,7 +141,7 @@ __host__ __device__ constexpr int stream_slots_per_item(int TB) { return stream_
 //          shortened passes (T < 4: one warp of the pair runs them alone) fit inside
 __host__ __device__ constexpr int stream_smem(int TB) {
     return stream_chained(TB)
-               ? ((stream_np(CHAIN_TW) + CHAIN_BANKS * stream_nw(CHAIN_TW) + CHAIN_D) * ROW_BYTES +
+               ? ((CHAIN_NP + CHAIN_BANKS * stream_nw(CHAIN_TW) + CHAIN_D) * ROW_BYTES +
                   (stream_nw(CHAIN_TW) + 2 * CHAIN_D) * 8 + 127) / 128 * 128
                : ((stream_np(TB) + stream_nw(TB)) * ROW_BYTES + stream_nw(TB) * 8 + 127) / 128 * 128;
 }
@@ -192,6 +211,23 @@ __device__ __forceinline__ void issue_row(const SCtx &c, double *rbank, int64_t 
     mbar_expect_tx(bar, 2 * ROW_BYTES);
     bulk_load(c.pring + (slot % NP) * SW, c.pin + off, ROW_BYTES, bar);
     bulk_load(rbank + slot * SW, c.rhs + off, ROW_BYTES, bar);
+}
+
+// request the rows at offset `off` and one pitch further (both arrays) into rhs slots `slot`,
+// `slot + 1` of bank `rbank` and the same slots of the p ring: ONE mbarrier (that of `slot`)
+// for the four copies; v0 / v1: the row exists.  One lane only.
+__device__ __forceinline__ void issue_rows2(const SCtx &c, double *rbank, int64_t off, int slot,
+                                            bool v0, bool v1) {
+    uint64_t *bar = c.bar + slot;
+    mbar_expect_tx(bar, ((v0 ? 1 : 0) + (v1 ? 1 : 0)) * 2 * ROW_BYTES);
+    if (v0) {
+        bulk_load(c.pring + slot * SW, c.pin + off, ROW_BYTES, bar);
+        bulk_load(rbank + slot * SW, c.rhs + off, ROW_BYTES, bar);
+    }
+    if (v1) {
+        bulk_load(c.pring + (slot + 1) * SW, c.pin + off + c.pitch, ROW_BYTES, bar);
+        bulk_load(rbank + (slot + 1) * SW, c.rhs + off + c.pitch, ROW_BYTES, bar);
+    }
 }
 
 // The two cells of one colour in a lane's two column pairs.  SET 0: the first cells A0, B0
@@ -487,13 +523,188 @@ __device__ __forceinline__ void stream_tick(double (&W)[2 * T + 4][4], double (&
     }
 }
 
+
+// One tick of a chain warp: TWO rows.  Rows R (register slot U, even) and R + 1 arrive; for
+// k = 0..T-1 the red half-sweep of sweep k runs on rows R - 2k and R - 2k - 1, then the black
+// one on rows R - 2k - 1 and R - 2k - 2 (the single-row ticks R and R + 1 merged: the two
+// rows of a half-sweep do not depend on each other).  TAIL then takes the late red residuals of
+// the last sweep on rows R - 2T, R - 2T - 1 and stores rows R - 2T - 2, R - 2T - 1; HEAD
+// hands the pair R - 2T, R - 2T + 1 to TAIL.  Same window of 2T + 4 rows as the single-row tick.
+template <int T, bool STEADY, int WALL, int ROLE, int KB>
+__device__ __forceinline__ void stream_tick2(double (&W)[2 * T + 4][4], double (&C)[T][2],
+                                             double (&FR)[2][2], double (&accA)[T + 1],
+                                             double (&accB)[T + 1], const int U, const int R,
+                                             const int64_t roff, const uint32_t ph, const int it,
+                                             const SCtx &c, const StreamPeers &pe) {
+    constexpr int NW = stream_nw(T), PF = CHAIN_PF;
+    constexpr int AB = KB > 0 ? KB - 1 : 0;
+    constexpr int D = CHAIN_D;
+    static_assert(NW == CHAIN_NP, "p ring slot = rhs slot");
+    const RbConsts &k = c.k;
+    // use n of hand-over slot h holds rows rs + n D + h (+1); for the pair in register slot U'
+    // of this loop iteration n = it (NW / D) + floor(U' / D): parity needs `ph` iff NW / D is odd
+    const uint32_t itpar = (NW / D) % 2 ? ph : 0u;
+    auto load2 = [&](const double *src, bool v0, bool v1) {
+        if (v0) {
+            const double2 a = *reinterpret_cast<const double2 *>(src);
+            const double2 b = *reinterpret_cast<const double2 *>(src + 64);
+            W[U][0] = a.x; W[U][1] = a.y; W[U][2] = b.x; W[U][3] = b.y;
+        } else {
+            W[U][0] = W[U][1] = W[U][2] = W[U][3] = 0.0;
+        }
+        if (v1) {
+            const double2 a = *reinterpret_cast<const double2 *>(src + SW);
+            const double2 b = *reinterpret_cast<const double2 *>(src + SW + 64);
+            W[U + 1][0] = a.x; W[U + 1][1] = a.y; W[U + 1][2] = b.x; W[U + 1][3] = b.y;
+        } else {
+            W[U + 1][0] = W[U + 1][1] = W[U + 1][2] = W[U + 1][3] = 0.0;
+        }
+    };
+    // ---- rows R, R + 1: requested (HEAD: rows R + PF, R + PF + 1 go out) or handed over ------
+    __syncwarp();  // every lane is done with the slots the request overwrites
+    if constexpr (ROLE != ROLE_TAIL) {
+        double *bank = U + PF < NW ? c.rr_cur : c.rr_next;
+        if (STEADY) {
+            if (elect_one()) issue_rows2(c, bank, roff + PF * c.pitch, (U + PF) % NW, true, true);
+        } else if (c.lane == 0) {
+            const bool v0 = R + PF < c.re, v1 = R + PF + 1 < c.re;
+            if (v0 || v1) issue_rows2(c, bank, roff + PF * c.pitch, (U + PF) % NW, v0, v1);
+        }
+        const bool l0 = STEADY || (R >= c.first && R < c.re);
+        const bool l1 = STEADY || (R + 1 >= c.first && R + 1 < c.re);
+        if (l0 || l1) mbar_wait(c.bar + U, ph);
+        load2(c.pl + U * SW, l0, l1);
+    } else {
+        if (STEADY || R < c.hend) {
+            mbar_wait(c.hfull + U % D, (itpar ^ (uint32_t)(U / D)) & 1u);
+            load2(c.hring + (U % D) * SW, true, true);
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(c.hempty + U % D);
+        } else {
+            load2(c.hring, false, false);
+        }
+    }
+    double fre_a = 0.0, fre_b = 0.0, fro_a = 0.0, fro_b = 0.0;  // red rhs of the last red half-sweep
+#pragma unroll
+    for (int kk = 0; kk < T; kk++) {
+        const int g = KB + kk;                      // sweep index in the pass
+        const int lv = (g > 0 ? g - 1 : 0) - AB;    // accumulator of the late red residuals
+        const int se = (U + 2 * NW - 2 * kk) % NW;          // even row R - 2kk
+        const int so = (U + 2 * NW - 2 * kk - 1) % NW;      // odd row R - 2kk - 1
+        const int se2 = (U + 2 * NW - 2 * kk - 2) % NW;     // even row R - 2kk - 2
+        const double *rpe = (U >= 2 * kk ? c.rl_cur : c.rl_prev) + se * SW;
+        const double *rpo = (U >= 2 * kk + 1 ? c.rl_cur : c.rl_prev) + so * SW;
+        const double2 rAe = *reinterpret_cast<const double2 *>(rpe);
+        const double2 rBe = *reinterpret_cast<const double2 *>(rpe + 64);
+        const double2 rAo = *reinterpret_cast<const double2 *>(rpo);
+        const double2 rBo = *reinterpret_cast<const double2 *>(rpo + 64);
+        // ---- red half-sweep of sweep kk: first cells of the even row, second cells of the odd
+        half_sweep<T, STEADY, WALL, 0, true>(W, se, R - 2 * kk, g, rAe.x, rBe.x, accA[lv], accB[lv], c);
+        half_sweep<T, STEADY, WALL, 1, true>(W, so, R - 2 * kk - 1, g, rAo.y, rBo.y, accA[lv], accB[lv], c);
+        // ---- black half-sweep: first cells of the odd row (rhs read above), second cells of the
+        //      even row below it (rhs carried from the tick before)
+        half_sweep<T, STEADY, WALL, 0, false>(W, so, R - 2 * kk - 1, g, rAo.x, rBo.x, accA[g - AB],
+                                              accB[g - AB], c);
+        half_sweep<T, STEADY, WALL, 1, false>(W, se2, R - 2 * kk - 2, g, C[kk][0], C[kk][1],
+                                              accA[g - AB], accB[g - AB], c);
+        C[kk][0] = rAe.y;
+        C[kk][1] = rBe.y;
+        if (kk == T - 1) { fre_a = rAe.x; fre_b = rBe.x; fro_a = rAo.y; fro_b = rBo.y; }
+    }
+    // ---- residual of the red cells of the LAST sweep of the pass on rows R - 2T (even) and
+    //      R - 2T - 1 (odd); their red rhs values were read one tick ago (FR) -----------------
+    if constexpr (ROLE != ROLE_HEAD) {
+#ifndef SB_STREAM_NOCOMPUTE
+        {
+            const int s = (U + 2 * NW - 2 * T) % NW, sm = (s + NW - 1) % NW, sp = (s + 1) % NW;
+            const int q = R - 2 * T;
+            if (STEADY || (unsigned)(q - c.cx0) < (unsigned)(c.cx1 - c.cx0)) {  // warp-uniform
+                double na, nb;
+                nbr2<0>(c, W[s], na, nb);
+                double ra = fma(-k.diag, W[s][0], tsum(k, W[sp][0] + W[sm][0], W[s][1] + na, FR[0][0]));
+                double rb = fma(-k.diag, W[s][2], tsum(k, W[sp][2] + W[sm][2], W[s][3] + nb, FR[0][1]));
+                if (WALL) ra = c.keepA ? 0.0 : ra;
+                accA[KB + T - 1 - AB] = fma(ra, ra, accA[KB + T - 1 - AB]);
+                accB[KB + T - 1 - AB] = fma(rb, rb, accB[KB + T - 1 - AB]);
+            }
+        }
+        {
+            const int s = (U + 2 * NW - 2 * T - 1) % NW, sm = (s + NW - 1) % NW, sp = (s + 1) % NW;
+            const int q = R - 2 * T - 1;
+            if (STEADY || (unsigned)(q - c.cx0) < (unsigned)(c.cx1 - c.cx0)) {  // warp-uniform
+                double na, nb;
+                nbr2<1>(c, W[s], na, nb);
+                double ra = fma(-k.diag, W[s][1], tsum(k, W[sp][1] + W[sm][1], W[s][0] + na, FR[1][0]));
+                double rb = fma(-k.diag, W[s][3], tsum(k, W[sp][3] + W[sm][3], W[s][2] + nb, FR[1][1]));
+                if (WALL) rb = c.keepB ? 0.0 : rb;
+                accA[KB + T - 1 - AB] = fma(ra, ra, accA[KB + T - 1 - AB]);
+                accB[KB + T - 1 - AB] = fma(rb, rb, accB[KB + T - 1 - AB]);
+            }
+        }
+#endif
+        FR[0][0] = fre_a; FR[0][1] = fre_b;
+        FR[1][0] = fro_a; FR[1][1] = fro_b;
+    }
+    // ---- retire ---------------------------------------------------------------------------
+    if constexpr (ROLE == ROLE_HEAD) {
+        // rows R - 2T, R - 2T + 1 have seen all of HEAD's half-sweeps: to TAIL, every pair from
+        // rs on in order.  Pair q is use n = it (NW / D) + floor((U - 2T) / D) of its slot, which
+        // is free once TAIL has read use n - 1
+        const int s0 = (U + 2 * NW - 2 * T) % NW, s1 = (s0 + 1) % NW;
+        const int q = R - 2 * T;
+        const int d = U - 2 * T;
+        const int hs = ((d % D) + D) % D;
+        const int nrel = (d - hs) / D;                           // floor(d / D)
+        if (STEADY || (q >= c.rs && q < c.hend)) {
+            if (STEADY || it * (NW / D) + nrel >= 1)
+                mbar_wait(c.hempty + hs, (itpar + (uint32_t)(nrel + 2 * (NW / D) + 1)) & 1u);
+            double *dst = c.hring + hs * SW;
+            *reinterpret_cast<double2 *>(dst) = make_double2(W[s0][0], W[s0][1]);
+            *reinterpret_cast<double2 *>(dst + 64) = make_double2(W[s0][2], W[s0][3]);
+            *reinterpret_cast<double2 *>(dst + SW) = make_double2(W[s1][0], W[s1][1]);
+            *reinterpret_cast<double2 *>(dst + SW + 64) = make_double2(W[s1][2], W[s1][3]);
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(c.hfull + hs);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {   // rows R - 2T - 2, R - 2T - 1: nothing reads them any more
+            const int lag = 2 * T + 2 - j;
+            const int s = (U + 2 * NW - lag) % NW;
+            const int q = R - lag;
+            if (STEADY || (unsigned)(q - c.x0) < (unsigned)(c.x1 - c.x0)) {
+                double *dst = c.pout + (roff - lag * c.pitch);
+                if (c.cmA) stg_f64x2(dst, W[s][0], W[s][1]);
+                if (c.cmB) stg_f64x2(dst + 64, W[s][2], W[s][3]);
+                // halo exchange fused into the pass: the rows within H of a slab edge also go
+                // straight into the neighbour's halo rows (the steady range keeps clear of them)
+                if (!STEADY) {
+                    const bool to_lo = pe.lo_p[0] != nullptr && q < pe.own0 + pe.H;
+                    const bool to_hi = pe.hi_p[0] != nullptr && q >= pe.own1 - pe.H;
+                    if (to_lo || to_hi) {  // warp-uniform, rare: 2H rows per slab and strip
+                        const int dstbuf = pe.ctl->src ^ 1;
+                        const int64_t rowshift = to_lo ? pe.lo_row0 - pe.own0
+                                                       : pe.hi_row0 - (pe.own1 - pe.H);
+                        double *peer = (to_lo ? pe.lo_p[dstbuf] : pe.hi_p[dstbuf]) +
+                                       (dst - pe.pbuf[dstbuf]) + rowshift * c.pitch;
+                        if (c.cmA) stg_f64x2(peer, W[s][0], W[s][1]);
+                        if (c.cmB) stg_f64x2(peer + 64, W[s][2], W[s][3]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // One work item (ROLE_SOLO) or one warp's half of it (chain).  TP = sweeps of the whole pass
 // (levels written); `partial` = this warp's slot of level 0.
 template <int T, int WALL, int ROLE, int KB, int TP>
 __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
                                             double *__restrict__ partial, int64_t part_stride,
                                             const StreamPeers &pe) {
-    constexpr int NW = stream_nw(T), NP = stream_np(T), PF = stream_pf(T);
+    constexpr bool ROWS2 = ROLE != ROLE_SOLO;   // chain warps: two rows per tick
+    constexpr int NW = stream_nw(T), NP = stream_np(T);
+    constexpr int PF = ROWS2 ? CHAIN_PF : stream_pf(T);
     constexpr int HP = 2 * TP + 2;          // warm-up rows of the whole pass
     constexpr int AB = KB > 0 ? KB - 1 : 0;
     constexpr int NBANK = ROLE == ROLE_SOLO ? 1 : CHAIN_BANKS;
@@ -506,7 +717,7 @@ __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
     // TAIL reads rows up to its last tick; HEAD hands over exactly those, the others retire
     // the stored rows
     c.hend = min(c.re, c.x1 + 2 * T + 2);
-    c.rend = (ROLE == ROLE_HEAD ? c.hend : c.x1) + 2 * T + 2;
+    c.rend = ROLE == ROLE_HEAD ? c.hend + 2 * T : c.x1 + 2 * T + 2;
     c.bc_lo = lo ? c.x0 : -(1 << 29);
     c.bc_hi = hi ? c.x1 - 1 : (1 << 29);
     c.cx0 = c.x0 + (lo ? 1 : 0);
@@ -522,8 +733,13 @@ __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
     const int hi_beg = pe.hi_p[0] != nullptr ? pe.own1 - pe.H : INT_MAX - 64;
     int st_lo = max(c.x0 + (lo ? 2 : 0), lo_end) + 2 * T + 2;
     int st_hi = min(min(c.x1 - (hi ? 2 : 0), c.re - PF - 1), hi_beg + 2 * T + 1);
-    if (ROLE != ROLE_SOLO) st_lo = max(st_lo, rs + 2 * NW);
-    if (ROLE == ROLE_TAIL) st_hi = min(c.x1 - (hi ? 2 : 0), hi_beg + 2 * T + 1);
+    if (ROWS2) {
+        // a two-row tick R sweeps rows R .. R - 2T - 1, stores R - 2T - 2 and R - 2T - 1 and
+        // requests rows up to R + PF + 1; the last tick of a loop iteration is R0 + NW - 2
+        st_lo = max(st_lo, rs + 2 * NW);
+        st_hi = min(c.x1 - 1 - (hi ? 2 : 0), hi_beg + 2 * T) + 1;
+        if (ROLE == ROLE_HEAD) st_hi = min(st_hi, c.re - PF - 2 + 1);
+    }
     if (ROLE != ROLE_TAIL && c.lane == 0) {
         for (int i = 0; i < NW; i++) mbar_init(c.bar + i, 1);
         if (ROLE == ROLE_HEAD)
@@ -533,8 +749,15 @@ __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
             }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // tick R requests row R + PF: rows below rs + PF are requested here (bank 0)
-        for (int r = c.first; r < rs + PF; r++)
-            if (r < c.re) issue_row<NP>(c, c.rring, (int64_t)r * c.pitch, r - rs);
+        if (ROWS2) {
+            for (int r = rs; r < rs + PF; r += 2) {
+                const bool v0 = r >= c.first && r < c.re, v1 = r + 1 >= c.first && r + 1 < c.re;
+                if (v0 || v1) issue_rows2(c, c.rring, (int64_t)r * c.pitch, r - rs, v0, v1);
+            }
+        } else {
+            for (int r = c.first; r < rs + PF; r++)
+                if (r < c.re) issue_row<NP>(c, c.rring, (int64_t)r * c.pitch, r - rs);
+        }
     }
     __syncwarp();
     // TAIL may touch the rings once HEAD has initialised the mbarriers
@@ -565,10 +788,16 @@ __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
         if (R0 >= st_lo && R0 + NW - 1 <= st_hi) {
             do {  // the steady state: straight-line code, no row tests
 #pragma unroll
-                for (int U = 0; U < NW; U++) {
-                    stream_tick<T, true, WALL, ROLE, KB>(W, C, FR, accA, accB, U, R0 + U, roff, ph, it,
-                                                         c, pe);
-                    roff += c.pitch;
+                for (int U = 0; U < NW; U += ROWS2 ? 2 : 1) {
+                    if constexpr (ROWS2) {
+                        stream_tick2<T, true, WALL, ROLE, KB>(W, C, FR, accA, accB, U, R0 + U, roff, ph,
+                                                              it, c, pe);
+                        roff += 2 * c.pitch;
+                    } else {
+                        stream_tick<T, true, WALL, ROLE, KB>(W, C, FR, accA, accB, U, R0 + U, roff, ph,
+                                                             it, c, pe);
+                        roff += c.pitch;
+                    }
                 }
                 ph ^= 1u;
                 it++;
@@ -578,11 +807,17 @@ __device__ __forceinline__ void stream_item(SCtx &c, int flags, int gpar,
             } while (true);
         } else {
 #pragma unroll
-            for (int U = 0; U < NW; U++) {
+            for (int U = 0; U < NW; U += ROWS2 ? 2 : 1) {
                 if (R0 + U >= c.rend) break;
-                stream_tick<T, false, WALL, ROLE, KB>(W, C, FR, accA, accB, U, R0 + U, roff, ph, it, c,
-                                                      pe);
-                roff += c.pitch;
+                if constexpr (ROWS2) {
+                    stream_tick2<T, false, WALL, ROLE, KB>(W, C, FR, accA, accB, U, R0 + U, roff, ph, it,
+                                                           c, pe);
+                    roff += 2 * c.pitch;
+                } else {
+                    stream_tick<T, false, WALL, ROLE, KB>(W, C, FR, accA, accB, U, R0 + U, roff, ph, it,
+                                                          c, pe);
+                    roff += c.pitch;
+                }
             }
             ph ^= 1u;
             it++;
@@ -649,7 +884,7 @@ sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict
         // then the mbarriers
         const int tw = chain_now ? CHAIN_TW : T;
         c.pring = reinterpret_cast<double *>(base);
-        c.rring = c.pring + stream_np(tw) * SW;
+        c.rring = c.pring + (chain_now ? CHAIN_NP : stream_np(tw)) * SW;
         c.hring = c.rring + (chain_now ? CHAIN_BANKS : 1) * stream_nw(tw) * SW;
         c.bar = reinterpret_cast<uint64_t *>(c.hring + (chain_now ? CHAIN_D : 0) * SW);
         c.hfull = c.bar + stream_nw(tw);
