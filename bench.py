@@ -359,6 +359,8 @@ def run_ours(args):
     nx, ny = wl["size"]
     mode = SOR_RED_BLACK if args.mode == "rb" else SOR_REFERENCE_ORDER
     ext = dict(sor_mode=mode, temporal_block=args.tblock, device=local_rank)
+    if args.tau > 0:
+        ext["tau"] = args.tau     # extension A9: adaptive time step (max |u|, |v| reductions)
     from stroemung_b200 import multi
     # N > 1: one row slab per rank, connected GPU-to-GPU (CUDA IPC over NVLink); the host
     # group only carries the connection blobs (stroemung_b200/multi.py)
@@ -565,7 +567,7 @@ def run_ours(args):
                    "initial_state": "fields at rest (p = u = v = 0; the inflow starts the flow); "
                                     "f64 arithmetic time does not depend on the values, and "
                                     "`verify` below runs the same kernels from a random state",
-                   "temporal_block": T, "sweeps_per_tick": k_avg,
+                   "temporal_block": T, "sweeps_per_tick": k_avg, "tau": args.tau,
                    "slabs": f"{n_gpus} row slab(s) along x",
                    "rb_plan": {"tile_kernel_tiles": rb_plan[0], "stream_items": rb_plan[1]}
                    if rb_plan and sor_path == 0 else None,
@@ -610,6 +612,8 @@ def main():
     ap.add_argument("--size", type=int, nargs=2, default=None)
     ap.add_argument("--mode", default="rb", choices=["rb", "lex"])
     ap.add_argument("--tblock", type=int, default=0)
+    ap.add_argument("--tau", type=float, default=0.0,
+                    help="> 0: adaptive time step (extension A9; the reference has none)")
     ap.add_argument("--e2e-depth", type=int, default=3,
                     help="requests in flight in the end-to-end leg at N = 1 (1 = serial)")
     ap.add_argument("--no-cpu", action="store_true")

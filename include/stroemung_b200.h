@@ -179,6 +179,11 @@ sb_status sb_get_state(sb_sim *sim, sb_state *state);
 sb_status sb_set_params(sb_sim *sim, const sb_params *params);
 /* replace the sparse velocity table (after sb_upload(SB_FIELD_KIND)) */
 sb_status sb_set_boundary_velocities(sb_sim *sim, const sb_boundary_velocity *v, size_t n);
+/* read it back (the `velocity` payload of the Inflow cells, src/cell.rs:12-16, that
+ * `#[derive(Serialize)]` writes with the cell types): up to `capacity` entries into v (may
+ * be NULL), the table's length into *n */
+sb_status sb_get_boundary_velocities(sb_sim *sim, sb_boundary_velocity *v, size_t capacity,
+                                     size_t *n);
 
 /* SimulationGrid::rebuild_boundary_list (src/grid/mod.rs:202-235), called after
  * sb_upload(SB_FIELD_KIND, ..) as src/lib.rs:70 does.  On SB_BOUNDARY_TOO_THIN the

@@ -66,7 +66,7 @@ SYMBOLS = [
     "sb_calculate_norm_squared", "sb_solve_sor", "sb_set_u_and_v",
     "sb_calculate_pressure_range", "sb_calculate_speed_range", "sb_sor_sweeps", "sb_download",
     "sb_upload", "sb_host_alloc", "sb_host_free", "sb_get_state", "sb_set_params",
-    "sb_set_boundary_velocities", "sb_rebuild_boundary_list", "sb_boundary_list",
+    "sb_set_boundary_velocities", "sb_get_boundary_velocities", "sb_rebuild_boundary_list", "sb_boundary_list",
     "sb_edit_cells", "sb_render_rgba", "sb_create_preset", "sb_error_cell", "sb_last_error_string",
     "sb_slab_export", "sb_slab_connect", "sb_slab_sync_halos", "sb_du2dx", "sb_duvdx", "sb_duvdy",
     "sb_dv2dy", "sb_laplacian", "sb_residual", "sb_calculate_f", "sb_calculate_g",
@@ -110,6 +110,8 @@ def lib():
         "sb_get_state": ([vp, C.POINTER(State)], C.c_int),
         "sb_set_params": ([vp, C.POINTER(Params)], C.c_int),
         "sb_set_boundary_velocities": ([vp, C.POINTER(BoundaryVelocity), C.c_size_t], C.c_int),
+        "sb_get_boundary_velocities": ([vp, C.POINTER(BoundaryVelocity), C.c_size_t,
+                                        C.POINTER(C.c_size_t)], C.c_int),
         "sb_rebuild_boundary_list": ([vp], C.c_int),
         "sb_boundary_list": ([vp, u64p, u8p, C.c_uint64, u64p], C.c_int),
         "sb_edit_cells": ([vp, C.c_uint64, C.c_uint64, C.c_uint8, d, d, i32p], C.c_int),

@@ -844,6 +844,14 @@ sb_status sb_set_boundary_velocities(sb_sim *sim, const sb_boundary_velocity *v,
     return apply_velocity_table(sim);
 }
 
+sb_status sb_get_boundary_velocities(sb_sim *sim, sb_boundary_velocity *v, size_t capacity,
+                                     size_t *n) {
+    if (!sim || !n) return SB_INVALID_ARGUMENT;
+    *n = sim->velocities.size();
+    if (v) std::copy_n(sim->velocities.begin(), std::min(capacity, sim->velocities.size()), v);
+    return SB_OK;
+}
+
 sb_status sb_rebuild_boundary_list(sb_sim *sim) {
     SB_ENTER(sim);
     sb_status st;

@@ -132,3 +132,90 @@ def simulation_to_json(prm, grid):
             "cell_type": cells_to_json(grid["kind"], grid["bu"], grid["bv"]),
         },
     }
+
+
+# ---- binary sidecar (extension) -----------------------------------------------------------
+# serde_json text costs ~20 bytes per f64 and minutes of parsing at 8192^2 (3 x 67 M values),
+# so for large grids the arrays move into ONE little-endian binary file next to the JSON
+# document and the document keeps everything else of the reference's format.  An array
+# document then reads {"v": 1, "dim": [nx, ny], "sidecar": {"file": name, "offset": bytes,
+# "dtype": "<f8"}} instead of carrying "data"; the cell types are u8 kinds (0 Fluid, 1 NoSlip,
+# 2 Outflow, 3 Inflow, 4 MovingWall) plus the sparse list "velocities": [[x, y, u, v], ..] of
+# the cells that carry one (src/cell.rs:12-16).  Documents without "sidecar" entries are the
+# reference's own format and load in the reference unchanged.
+SIDECAR_MIN_CELLS = 1 << 18     # grids from 512 x 512 on use the sidecar by default
+
+
+def _resolve_array(doc, base_dir):
+    """array document (inline or sidecar) -> ndarray"""
+    import os
+    if "sidecar" not in doc:
+        return array_from_json(doc)
+    sc = doc["sidecar"]
+    nx, ny = doc["dim"]
+    return np.fromfile(os.path.join(base_dir, sc["file"]), dtype=np.dtype(sc["dtype"]),
+                       count=nx * ny, offset=sc["offset"]).reshape(nx, ny)
+
+
+def save_simulation(path, prm, grid, sidecar=None):
+    """Write the simulation as the reference's JSON document (`path`).  sidecar: True / False /
+    None (= by size): arrays go to `path + ".bin"`.  Returns the document written."""
+    import os
+    nx, ny = prm["size"]
+    if sidecar is None:
+        sidecar = nx * ny >= SIDECAR_MIN_CELLS
+    if not sidecar:
+        doc = simulation_to_json(prm, grid)
+        with open(path, "w") as f:
+            json.dump(doc, f)
+        return doc
+    bin_name = os.path.basename(path) + ".bin"
+    doc = simulation_to_json(prm, {"p": np.zeros((0, 0)), "u": np.zeros((0, 0)),
+                                   "v": np.zeros((0, 0)), "kind": np.zeros((0, 0), np.uint8),
+                                   "bu": np.zeros((0, 0)), "bv": np.zeros((0, 0))})
+    offset = 0
+    with open(path + ".bin", "wb") as f:
+        for key, name in (("pressure", "p"), ("u", "u"), ("v", "v")):
+            a = np.ascontiguousarray(grid[name], dtype="<f8")
+            assert a.shape == (nx, ny), (name, a.shape)
+            doc["grid"][key] = {"v": 1, "dim": [nx, ny],
+                                "sidecar": {"file": bin_name, "offset": offset, "dtype": "<f8"}}
+            f.write(a.tobytes())
+            offset += a.nbytes
+        kind = np.ascontiguousarray(grid["kind"], dtype=np.uint8)
+        doc["grid"]["cell_type"] = {
+            "v": 1, "dim": [nx, ny],
+            "sidecar": {"file": bin_name, "offset": offset, "dtype": "|u1"},
+            "velocities": [[int(x), int(y), float(grid["bu"][x, y]), float(grid["bv"][x, y])]
+                           for x, y in zip(*np.nonzero((kind == KIND_INFLOW) |
+                                                       (kind == KIND_MOVING_WALL)))]}
+        f.write(kind.tobytes())
+    with open(path, "w") as f:
+        json.dump(doc, f)
+    return doc
+
+
+def load_simulation(path, quirk_serde_json=False):
+    """(params dict, grid dict) of a document written by the reference or by save_simulation."""
+    import os
+    with open(path) as f:
+        doc = loads(f.read(), quirk_serde_json=quirk_serde_json)
+    base = os.path.dirname(os.path.abspath(path))
+    g = doc["grid"]
+    if "sidecar" not in g["cell_type"]:
+        return simulation_from_json(doc)
+    nx, ny = g["cell_type"]["dim"]
+    kind = _resolve_array(g["cell_type"], base).astype(np.uint8)
+    bu, bv = np.zeros((nx, ny)), np.zeros((nx, ny))
+    for x, y, a, b in g["cell_type"].get("velocities", []):
+        bu[x, y], bv[x, y] = a, b
+    grid = {"size": tuple(g["size"]), "p": _resolve_array(g["pressure"], base),
+            "u": _resolve_array(g["u"], base), "v": _resolve_array(g["v"], base),
+            "kind": kind, "bu": bu, "bv": bv}
+    prm = {"size": tuple(doc["size"]), "cell_size": tuple(doc["cell_size"]), "delt": doc["delt"],
+           "gamma": doc["gamma"], "reynolds": doc["reynolds"],
+           "initial_norm_squared": doc.get("initial_norm_squared"),
+           "sor_absolute_epsilon": doc["sor_absolute_epsilon"],
+           "max_iterations": doc["max_iterations"], "iterations": doc["iterations"],
+           "time": doc["time"], "omega": doc["omega"]}
+    return prm, grid

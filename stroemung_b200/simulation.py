@@ -195,6 +195,49 @@ class Simulation:
         return cls.try_from(prm, **ext)
 
     @classmethod
+    def load(cls, path, quirk_serde_json=False, **ext):
+        """A document of the reference (`serde_json::to_writer(.., &simulation)`) or of
+        `save` (binary sidecar for the arrays of large grids, refjson.save_simulation)."""
+        prm, grid = refjson.load_simulation(path, quirk_serde_json=quirk_serde_json)
+        prm["grid"] = grid
+        return cls.try_from(prm, **ext)
+
+    # `#[derive(Serialize)] Simulation` (src/simulation.rs:49-69): f, g, rhs and the boundary
+    # list are skipped, the grid writes pressure / u / v / cell_type (src/grid/mod.rs:112-125)
+    def _host_state(self):
+        assert self._prm.world <= 1, "serialise a slab run through stroemung_b200.multi.gather_field"
+        L = _capi.lib()
+        st = self._state()
+        n = C.c_size_t()
+        self._check(L.sb_get_boundary_velocities(self._h, None, 0, C.byref(n)))
+        tab = (_capi.BoundaryVelocity * max(n.value, 1))()
+        self._check(L.sb_get_boundary_velocities(self._h, tab, n.value, C.byref(n)))
+        kind = self.grid.cell_type
+        bu, bv = np.zeros(kind.shape), np.zeros(kind.shape)
+        for i in range(n.value):
+            x, y = int(tab[i].x), int(tab[i].y)
+            if kind[x, y] in (_capi.KIND_INFLOW, _capi.KIND_MOVING_WALL):
+                bu[x, y], bv[x, y] = tab[i].u, tab[i].v
+        prm = {"size": self.size, "cell_size": self.cell_size, "delt": st.delt,
+               "gamma": self._prm.gamma, "reynolds": self._prm.reynolds,
+               "initial_norm_squared": st.initial_norm_squared if st.has_initial_norm else None,
+               "sor_absolute_epsilon": self._prm.sor_absolute_epsilon,
+               "max_iterations": int(self._prm.max_iterations), "iterations": int(st.iterations),
+               "time": st.time, "omega": self._prm.omega}
+        grid = {"p": self.grid.pressure, "u": self.grid.u, "v": self.grid.v, "kind": kind,
+                "bu": bu, "bv": bv}
+        return prm, grid
+
+    def to_json(self):
+        """The document `serde_json::to_value(&simulation)` gives (a dict)."""
+        return refjson.simulation_to_json(*self._host_state())
+
+    def save(self, path, sidecar=None):
+        """Write `to_json()` to `path`; large grids keep their arrays in `path + ".bin"`
+        (refjson.save_simulation).  Returns the document."""
+        return refjson.save_simulation(path, *self._host_state(), sidecar=sidecar)
+
+    @classmethod
     def from_preset(cls, preset, size, cell_size, delt, gamma, reynolds, sor_absolute_epsilon,
                     max_iterations, omega, preset_args=(), **ext):
         """Device-side mask generation (no host arrays): sb_create_preset."""

@@ -94,3 +94,66 @@ def test_pipeline_three_requests_in_flight():
         assert_bits_equal(views[1], o.u, f"u of request {r}")
         assert_bits_equal(views[2], o.v, f"v of request {r}")
     pipe.close()
+
+
+# ---- `#[derive(Serialize)] Simulation` on the GPU class --------------------------------------
+
+def test_to_json_matches_reference_serialize_snapshot(snapshots):
+    """src/simulation.rs:422-447: try_from(presets::empty([5, 7])) serialised ==
+    stroemung__simulation__tests__serialize.snap, from the DEVICE state (fields downloaded,
+    initial norm latched by sb_create)."""
+    g = presets_empty((5, 7))
+    unf = {"size": (5, 7), "cell_size": (1.0, 2.0), "delt": 1.4, "gamma": 1.7, "reynolds": 100.0,
+           "initial_norm_squared": None, "sor_absolute_epsilon": 0.001, "max_iterations": 100,
+           "iterations": 0, "time": 0.0, "omega": 1.7, "grid": g}
+    sim = Simulation.try_from(unf, sor_mode=SOR_REFERENCE_ORDER)
+    assert sim.to_json() == snapshots["stroemung__simulation__tests__serialize"]["json"]
+    sim.close()
+
+
+def presets_empty(size):
+    from stroemung_b200 import presets
+    return presets.empty(size)
+
+
+@pytest.mark.parametrize("sidecar", [False, True])
+def test_save_load_round_trip_and_continue(tmp_path, sidecar):
+    """tick, save (inline JSON / binary sidecar), load into a new handle, tick both: the same
+    bits, and the same as the oracle that never left memory"""
+    unf = case(96, 150, 8)
+    sim = Simulation.try_from(unf, sor_mode=SOR_RED_BLACK)
+    o = oracle_from(unf, sor_mode=po.SOR_RED_BLACK)
+    for _ in range(2):
+        sim.run_simulation_tick()
+        o.run_simulation_tick()
+    path = str(tmp_path / "state.json")
+    doc = sim.save(path, sidecar=sidecar)
+    assert (tmp_path / "state.json.bin").exists() == sidecar
+    assert doc["iterations"] == 2 and doc["time"] == o.state().time
+    assert doc["initial_norm_squared"] == sim.initial_norm_squared
+    sim2 = Simulation.load(path, sor_mode=SOR_RED_BLACK)
+    assert np.array_equal(sim2.grid.cell_type, sim.grid.cell_type)
+    for s_ in (sim, sim2):
+        it, nrm = s_.run_simulation_tick()
+        if s_ is sim:
+            oit, onrm = o.run_simulation_tick()
+        assert it == oit and abs(nrm - onrm) <= 1e-12 * abs(onrm)
+        assert_bits_equal(s_.grid.pressure, o.p, "p")
+        assert_bits_equal(s_.grid.u, o.u, "u")
+        assert_bits_equal(s_.grid.v, o.v, "v")
+    assert sim2.to_json() == sim.to_json()
+    sim.close()
+    sim2.close()
+
+
+def test_to_json_of_a_device_side_preset():
+    """sb_create_preset builds the mask on the device: the velocities of its Inflow cells come
+    back through sb_get_boundary_velocities and the document equals the host preset's"""
+    from stroemung_b200 import presets, refjson
+    size = (100, 20)
+    sim = Simulation.from_preset("obstacle", size, (0.1, 0.2), 0.005, 0.9, 100.0, 1e-3, 100, 1.7,
+                                 sor_mode=SOR_RED_BLACK)
+    g = presets.obstacle(size)
+    doc = sim.to_json()
+    assert doc["grid"]["cell_type"] == refjson.cells_to_json(g["kind"], g["bu"], g["bv"])
+    sim.close()
