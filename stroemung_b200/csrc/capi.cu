@@ -91,7 +91,7 @@ static void destroy(sb_sim *s) {
     cudaFree(s->bl.lin); cudaFree(s->bl.ke); cudaFree(s->bl.bu); cudaFree(s->bl.bv);
     cudaFree(s->bl.ru); cudaFree(s->bl.rv); cudaFree(s->bl.nu); cudaFree(s->bl.nv);
     cudaFree(s->bl.wu); cudaFree(s->bl.wv);
-    cudaFree(s->d_partial); cudaFree(s->d_scalars); cudaFree(s->d_ctl); cudaFree(s->d_lex_sync);
+    cudaFree(s->d_partial); cudaFree(s->d_scalars); cudaFree(s->d_ctl); cudaFree(s->d_lex_sync); cudaFree(s->d_lex_ll);
     cudaFree(s->d_scan); cudaFree(s->d_err);
     if (s->h_scalars) cudaFreeHost(s->h_scalars);
     if (s->h_ctl) cudaFreeHost(s->h_ctl);

@@ -185,8 +185,11 @@ struct sb_sim {
     double *d_scalars = nullptr;  // small device scratch (results of final reductions)
     double *h_scalars = nullptr;  // pinned mirror
     sb::SorCtl *d_ctl = nullptr, *h_ctl = nullptr;
-    int32_t *d_lex_sync = nullptr;  // wavefront kernel: ticket + per-band progress
+    int32_t *d_lex_sync = nullptr;  // wavefront kernel: the band ticket
     size_t lex_sync_cap = 0;
+    uint4 *d_lex_ll = nullptr;      // wavefront kernel: hand-over rows {lo, seq, hi, seq} per band
+    size_t lex_ll_cap = 0;
+    uint32_t lex_seq = 0;           // sweeps launched so far (tag of the hand-over elements)
     // classification scratch
     int64_t *d_scan = nullptr;
     size_t scan_cap = 0;
