@@ -156,13 +156,7 @@ static sb_status allocate(const sb_params *params, sb_sim **out) {
     g.gx0 = xb - s->halo;
     g.own0 = s->halo;
     g.own1 = s->halo + (xe - xb);
-    // rows start 128-byte aligned; a pitch that is a multiple of 4 KB would map the same
-    // column of consecutive rows to the same L1 set and L2 slice -- the reference-order sweep
-    // walks 32 rows per warp at one column (2.9 -> 0.x ms per sweep at 2048^2 without that
-    // aliasing, profiles/r2_lex_history.txt), the streaming pass gains ~1.5 % -- so such
-    // pitches get 256 bytes of padding
     g.pitch = round_up(g.NY, 16);
-    if (g.pitch % 512 == 0) g.pitch += 32;
     s->field_bytes = (size_t)g.nxl * g.pitch * sizeof(double);
     s->flag_bytes = (size_t)g.nxl * g.pitch;
 #define SB_TRY(call)                                                            \
