@@ -298,8 +298,16 @@ def verify_on_bench_grid(wl, mode, tblock, device, sweeps=8, tick_sweeps=4):
         return bool(np.array_equal(np.ascontiguousarray(a).view(np.uint64),
                                    np.ascontiguousarray(b).view(np.uint64)))
 
+    # norms: the oracle folds the squared residuals of all cells sequentially like the
+    # reference (src/simulation.rs:216-227), the GPU sums a tree; the sequential sum of N
+    # positive terms carries a rounding error of ~sqrt(N) ulp (9e-13 at 8192^2)
+    rtol = max(1e-12, 8.0 * np.sqrt(float(nx) * ny) * 2.0 ** -53)
+    worst = [0.0]
+
     def close(a, b):
-        return a == b or abs(a - b) <= 1e-12 * max(abs(a), abs(b))
+        if a != b:
+            worst[0] = max(worst[0], abs(a - b) / max(abs(a), abs(b)))
+        return a == b or abs(a - b) <= rtol * max(abs(a), abs(b))
 
     bad = []
     norms = sim.sor_sweeps(sweeps)
@@ -311,8 +319,10 @@ def verify_on_bench_grid(wl, mode, tblock, device, sweeps=8, tick_sweeps=4):
         bad.append("p after sweeps")
     it, nrm = sim.run_simulation_tick()
     oit, onrm = o.run_simulation_tick()
-    if it != oit or not close(nrm, onrm):
-        bad.append("tick (iterations, norm)")
+    if it != oit:
+        bad.append(f"tick iterations {it} vs {oit}")
+    if not close(nrm, onrm):
+        bad.append(f"tick norm {nrm!r} vs {onrm!r}")
     for name, a, b in (("p", sim.grid.pressure, o.p), ("u", sim.grid.u, o.u),
                        ("v", sim.grid.v, o.v)):
         if not same(a, b):
@@ -323,7 +333,7 @@ def verify_on_bench_grid(wl, mode, tblock, device, sweeps=8, tick_sweeps=4):
     return {"result": "bit-exact" if not bad else "MISMATCH: " + ", ".join(bad),
             "grid": [nx, ny], "sweeps": sweeps, "tick_sweeps": it,
             "fields": "p after sweeps; p, u, v after one tick (random initial p, u, v)",
-            "norm_rtol": 1e-12, "against": "oracle/stroemung_oracle.c "
+            "norm_rtol": rtol, "norm_rel_diff_max": worst[0], "against": "oracle/stroemung_oracle.c "
             + ("red-black restatement" if rb else "reference order"),
             "rb_plan": plan, "sor_path": path, "seconds": time.perf_counter() - t0}
 

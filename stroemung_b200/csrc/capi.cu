@@ -49,7 +49,6 @@ static DebugKnobs read_debug_knobs() {
     k.rb_frozen = geti("SB_RB_FROZEN", 1) != 0;
     if (const char *e = getenv("SB_WALL_WEIGHT")) k.wall_weight = atof(e);
     k.trace_plan = getenv("SB_DEBUG_PLAN") != nullptr;
-    k.trace_stream = getenv("SB_STREAM_TRACE") != nullptr;
     k.trace_mid = getenv("SB_MID_TRACE") != nullptr;
     k.trace_fin = getenv("SB_FIN_TRACE") != nullptr;
     return k;

@@ -139,7 +139,6 @@ struct DebugKnobs {
     bool rb_frozen = true;     // SB_RB_FROZEN=0: frozen tiles stay on the tile kernel
     double wall_weight = 0.0;  // SB_WALL_WEIGHT: plan weight of a wall row (0 = default)
     bool trace_plan = false;   // SB_DEBUG_PLAN
-    bool trace_stream = false; // SB_STREAM_TRACE
     bool trace_mid = false;    // SB_MID_TRACE
     bool trace_fin = false;    // SB_FIN_TRACE
 };

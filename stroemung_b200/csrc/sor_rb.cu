@@ -693,9 +693,10 @@ sb_status launch_sor_rb_pass(sb_sim *s, int *nparts_out, int norm_only, const Rb
     }
     if (fused) *fused = 0;
     if (n_items > 0) {
-        // single GPU: the streaming kernel's last CTA finalizes the pass (a slab run needs
-        // the all-gather of sor_finalize_kernel)
-        const RbFin *f = (fin && fused && !s->slab) ? fin : nullptr;
+        // the streaming kernel's last CTA finalizes the pass (row slabs: including the
+        // all-gather of the per-slab sums); sor_finalize_kernel only runs when there is no
+        // streaming item at all
+        const RbFin *f = (fin && fused) ? fin : nullptr;
         if ((st = launch_sor_rb_stream(s, n_tile, nparts, h, f))) return st;
         if (f) *fused = 1;
     }

@@ -48,6 +48,7 @@
 
 #include <algorithm>
 
+#include "slab_dev.cuh"
 #include "sor_rb.cuh"
 
 namespace sb {
@@ -851,7 +852,7 @@ __global__ void __launch_bounds__(32 * stream_warps(TB), 1)
 sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict__ pbuf,
                      const double *__restrict__ rhs, SorCtl *ctl, double *partial, int part_base,
                      int part_stride, int64_t pitch, int gpar, RbConsts k, RbFin fin,
-                     const __grid_constant__ StreamPeers pe) {
+                     const __grid_constant__ StreamPeers pe, const __grid_constant__ SlabLink lk) {
     constexpr bool CH = stream_chained(TB);
     constexpr int IPC = stream_items_per_cta(TB), SPI = stream_slots_per_item(TB);
     const int T = ctl->active_T;
@@ -925,12 +926,17 @@ sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict
     }
     // ---- the last CTA to finish totals the partials of the whole pass (tile kernel's
     //      included: it ran before), applies the exit rule and advances the control block --
-    //      what sor_finalize_kernel does as a separate launch (single GPU only) ---------------
+    //      what sor_finalize_kernel does as a separate launch.  Row slabs: the per-slab sums of
+    //      all ranks are gathered here too (slab_dev.cuh) and added in rank order, so every
+    //      rank takes the same exit decision; the round is also the release / acquire point of
+    //      the halo rows this kernel stored into the neighbours (system-scope fence below) ------
     if (!fin.enabled) return;
     __shared__ int s_last;
     __shared__ double s_sum[stream_warps(TB)];
     __shared__ double s_norm[RB_TMAX];
-    __threadfence();
+    __shared__ double s_gathered[SB_MAX_WORLD * 8];
+    if (lk.world > 1) __threadfence_system();
+    else __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(fin.counter, 1u) == gridDim.x - 1;
     __syncthreads();
@@ -946,10 +952,29 @@ sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict
         if (threadIdx.x == 0) {
             double t = 0.0;
             for (int w = 0; w < stream_warps(TB); w++) t += s_sum[w];
-            s_norm[lvl] = t / fin.fluid_cells;
+            s_norm[lvl] = t;
         }
         __syncthreads();
     }
+    if (lk.world > 1) {
+        const bool ok = slab_allgather(lk, s_norm, T, s_gathered);
+        if (!ok) {   // a peer went missing: end the solve, the host reports it
+            if (threadIdx.x == 0) {
+                ctl->active_T = 0;
+                ctl->finished = 1;
+                *fin.counter = 0u;
+            }
+            return;
+        }
+        if ((int)threadIdx.x < T) {
+            double t = s_gathered[threadIdx.x];
+            for (int r = 1; r < lk.world; r++) t += s_gathered[r * 8 + threadIdx.x];
+            s_norm[threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+    if ((int)threadIdx.x < T) s_norm[threadIdx.x] = s_norm[threadIdx.x] / fin.fluid_cells;
+    __syncthreads();
     if (threadIdx.x == 0) {
         sor_advance_ctl(ctl, s_norm, T, fin.initial_norm, fin.eps2, fin.test_exit, fin.norm_hist);
         *fin.counter = 0u;
@@ -957,7 +982,8 @@ sor_rb_stream_kernel(const RbItem *__restrict__ items, double *const *__restrict
 }
 
 using StreamKernel = void (*)(const RbItem *, double *const *, const double *, SorCtl *,
-                              double *, int, int, int64_t, int, RbConsts, RbFin, StreamPeers);
+                              double *, int, int, int64_t, int, RbConsts, RbFin, StreamPeers,
+                              SlabLink);
 StreamKernel stream_kernel(int TB) {
     switch (TB) {
     case 1: return sor_rb_stream_kernel<1>;
@@ -1430,9 +1456,12 @@ sb_status launch_sor_rb_stream(sb_sim *s, int part_base, int part_stride, int h,
     }
     pe.pbuf = rb_pbuf_ptr(s);
     pe.ctl = s->d_ctl;
+    SlabLink lk{};
+    lk.world = 1;
+    if (s->slab) lk = s->link;
     stream_kernel(TB)<<<s->plan.n_items / ipc, 32 * nw, stream_smem_bytes(TB), s->stream>>>(
         s->plan.d_items, rb_pbuf_ptr(s), s->rhs, s->d_ctl, s->d_partial, part_base, part_stride,
-        g.pitch, gpar, rb_consts(s), fin, pe);
+        g.pitch, gpar, rb_consts(s), fin, pe, lk);
     s->launches++;
     SB_CUDA(cudaGetLastError());
     return SB_OK;
