@@ -48,6 +48,7 @@ static DebugKnobs read_debug_knobs() {
     k.rb_stream_kinds = geti("SB_RB_STREAM_KINDS", 3);
     k.rb_frozen = geti("SB_RB_FROZEN", 1) != 0;
     if (const char *e = getenv("SB_WALL_WEIGHT")) k.wall_weight = atof(e);
+    if (const char *e = getenv("SB_PLAN_OVERHEAD")) k.plan_overhead = atof(e);
     k.trace_plan = getenv("SB_DEBUG_PLAN") != nullptr;
     k.trace_mid = getenv("SB_MID_TRACE") != nullptr;
     k.trace_fin = getenv("SB_FIN_TRACE") != nullptr;

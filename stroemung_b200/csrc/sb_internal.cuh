@@ -138,6 +138,7 @@ struct DebugKnobs {
     int rb_stream_kinds = 3;   // SB_RB_STREAM_KINDS: bit 0 wall strips, bit 1 boundary rows
     bool rb_frozen = true;     // SB_RB_FROZEN=0: frozen tiles stay on the tile kernel
     double wall_weight = 0.0;  // SB_WALL_WEIGHT: plan weight of a wall row (0 = default)
+    double plan_overhead = -1.0;   // SB_PLAN_OVERHEAD: rows charged per work item (< 0 = default)
     bool trace_plan = false;   // SB_DEBUG_PLAN
     bool trace_mid = false;    // SB_MID_TRACE
     bool trace_fin = false;    // SB_FIN_TRACE

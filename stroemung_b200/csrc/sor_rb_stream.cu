@@ -1184,14 +1184,12 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
     // runs of tiles of one item kind along x, per strip.  weight: how much longer a wall
     // strip takes per row than a plain one; its items get that much fewer rows
     struct Run { int tj, ti0, len, kind; double weight; };
-    // Wall items run 1.5x (one GPU) to 2.5x (a slab with a neighbour in front) slower per row
-    // than plain ones, and in a slab their total throughput hardly grows with the number of
-    // warps on them (per-item traces, profiles/r1_wall_strip_experiments.txt): there they must
-    // start with plenty of warps or they are the straggler every pass (weight 6: two slabs
-    // 14.7 -> 13.1 ms per tick).  On one GPU weight 2 balances them; a larger weight costs
-    // nothing on a wide grid (8192^2: 12.34 vs 12.40 ms) but 15 % on a narrow one (8192 x 2048:
-    // 2 of 19 strips are walls), so it stays at 2 there.
-    double wall_weight = s->slab ? 6.0 : 2.0;
+    // Wall items run ~1.5x slower per row than plain ones (their copy of the window carries
+    // the boundary refresh); weight 2 balances them on one GPU and in row slabs alike.  (With
+    // the one-warp T = 4 kernel of round 1 a slab needed weight 6 -- wall items were 2.5x slower
+    // there; with the two-warp chain weight 6 costs 10 % at two slabs:
+    // profiles/r2_wall_weight_slabs.txt.)
+    double wall_weight = 2.0;
     if (s->dbg.wall_weight > 0.0) wall_weight = s->dbg.wall_weight;
     std::vector<Run> runs;
     std::vector<int32_t> slow;
@@ -1249,6 +1247,10 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
                                                   stream_smem_bytes(T));
     if (ctas < 1) ctas = 1;
     const int64_t resident = (int64_t)dev_sms * ctas;  // CTAs at a time
+    // what an item costs beyond its rows and warm-up rows, in rows: pipeline fill and drain on
+    // the row-tested copy of the tick, ring set-up, and the CTA's warps waiting for its slowest
+    // item before the next wave's CTA can start (profiles/r2_plan_overhead.txt)
+    const double item_overhead = s->dbg.plan_overhead >= 0.0 ? s->dbg.plan_overhead : 100.0;
     auto pieces = [](const Run &r, int seg) {
         return std::max(1, std::min(r.len, (int)((r.len * r.weight + seg - 1) / seg)));
     };
@@ -1265,7 +1267,7 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
         const int64_t nc = (n[0] + nwarp - 1) / nwarp + (n[1] + nwarp - 1) / nwarp;
         if (nc == 0) break;
         const int64_t waves = (nc + resident - 1) / resident;
-        const double cost = (double)waves * (longest * BX + 2.0 * h);
+        const double cost = (double)waves * (longest * BX + 2.0 * h + item_overhead);
         if (cost < best_cost) { best_cost = cost; best_seg = seg; }
     }
     // Row-granular plan for ONE wave: split the resident CTAs between the two kinds, hand the
@@ -1320,7 +1322,8 @@ sb_status rb_ensure_plan(sb_sim *s, int BX, int BY, int h) {
                 }
                 for (size_t i = 0; i < runs.size(); i++)
                     if ((runs[i].kind != IT_PLAIN) == (k == 1))
-                        cost = std::max(cost, waves * ((run_rows(runs[i]) + m[i] - 1) / m[i] + 2.0 * h) *
+                        cost = std::max(cost, waves * ((run_rows(runs[i]) + m[i] - 1) / m[i] + 2.0 * h +
+                                                       item_overhead) *
                                                   runs[i].weight);
             }
             cost *= 1.0 + 0.03 * (waves - 1);   // ties go to fewer, longer items
