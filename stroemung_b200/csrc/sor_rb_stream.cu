@@ -18,7 +18,10 @@
 //     every row has a fixed register name); the only exchange between lanes is one shuffle
 //     per half-sweep (the y-neighbour across the lane boundary);
 //   * rows of p and rhs are fetched PF rows ahead by 1-D bulk copies of the TMA engine into
-//     per-warp shared-memory rings (one mbarrier per slot);
+//     per-item shared-memory rings (one mbarrier per slot);
+//   * at T = 4 the strip is walked by a CHAIN of two such warps (HEAD: sweeps 0-1, TAIL: sweeps
+//     2-3, rows handed over through a shared-memory ring; two rows per tick) -- see "two warps
+//     per work item" below;
 //   * residuals ride along exactly as in the tile kernel: black cells at their update, red
 //     cells of sweep k inside the red half-sweep of sweep k+1.
 //
