@@ -338,6 +338,52 @@ def verify_on_bench_grid(wl, mode, tblock, device, sweeps=8, tick_sweeps=4):
             "rb_plan": plan, "sor_path": path, "seconds": time.perf_counter() - t0}
 
 
+def _e2e_pipelined(sim, depth, args, fields, L, multi, group, wl, ext):
+    """N = 1 end-to-end leg: `depth` requests in flight through HostPipeline (sb_tick_host).
+    -> (seconds, steps in them, steps per request, description)"""
+    import threading
+    import time
+
+    from stroemung_b200.pipeline import HostPipeline
+    first = [sim]
+
+    def make_sim():
+        if first:
+            return first.pop()
+        return multi.from_preset(group, wl["preset"], wl["size"], wl["cell_size"],
+                                 wl["delt"], wl["gamma"], wl["reynolds"], wl["eps"],
+                                 wl["max_iterations"], wl["omega"],
+                                 preset_args=wl["preset_args"], **ext)
+    pipe = HostPipeline(make_sim, depth=depth)
+    req = [[pipe.alloc() for _ in range(3)] for _ in range(depth)]
+    for bufs in req:
+        for hbuf, fld in zip(bufs, fields):
+            sim._check(L.sb_download(sim._h, fld, hbuf))
+    e2e_steps = max(2, min(args.steps, 4))
+    for bufs in req:                      # one untimed step per request (first-touch)
+        pipe.submit(*bufs).result()
+
+    def drive(bufs):
+        for _ in range(e2e_steps):
+            pipe.submit(*bufs).result()   # H2D x3, tick, D2H x3 inside sb_tick_host
+    drivers = [threading.Thread(target=drive, args=(bufs,)) for bufs in req]
+    t0 = time.perf_counter()
+    for t in drivers:
+        t.start()
+    for t in drivers:
+        t.join()                          # every result() has synchronised its stream
+    dt_e2e = time.perf_counter() - t0
+    e2e_total = depth * e2e_steps
+    extra_sims = [s_ for s_ in pipe.sims if s_ is not sim]
+    pipe.sims = []                        # `sim` is closed below, the others here
+    pipe.close()
+    for s_ in extra_sims:
+        s_.close()
+    e2e_how = (f"{depth} requests in flight (HostPipeline: {depth} handles, streams and host "
+               f"threads, sb_tick_host), {e2e_steps} steps each; host clock around all of them")
+    return dt_e2e, e2e_total, e2e_steps, e2e_how
+
+
 # ---- our arm -----------------------------------------------------------------------------
 def run_ours(args):
     from stroemung_b200 import _capi
@@ -443,48 +489,16 @@ def run_ours(args):
     fields = (_capi.FIELD_P, _capi.FIELD_U, _capi.FIELD_V)
     sim_bytes = rows * ny * 57
     depth = 1 if world > 1 or args.e2e_depth == 1 or 3 * sim_bytes > 60e9 else args.e2e_depth
+    e2e_done = False
     if depth > 1:
-        import threading
-        import time
-
-        from stroemung_b200.pipeline import HostPipeline
-        first = [sim]
-
-        def make_sim():
-            if first:
-                return first.pop()
-            return multi.from_preset(group, wl["preset"], wl["size"], wl["cell_size"],
-                                     wl["delt"], wl["gamma"], wl["reynolds"], wl["eps"],
-                                     wl["max_iterations"], wl["omega"],
-                                     preset_args=wl["preset_args"], **ext)
-        pipe = HostPipeline(make_sim, depth=depth)
-        req = [[pipe.alloc() for _ in range(3)] for _ in range(depth)]
-        for bufs in req:
-            for hbuf, fld in zip(bufs, fields):
-                sim._check(L.sb_download(sim._h, fld, hbuf))
-        e2e_steps = max(2, min(args.steps, 4))
-        for bufs in req:                      # one untimed step per request (first-touch)
-            pipe.submit(*bufs).result()
-
-        def drive(bufs):
-            for _ in range(e2e_steps):
-                pipe.submit(*bufs).result()   # H2D x3, tick, D2H x3 inside sb_tick_host
-        drivers = [threading.Thread(target=drive, args=(bufs,)) for bufs in req]
-        t0 = time.perf_counter()
-        for t in drivers:
-            t.start()
-        for t in drivers:
-            t.join()                          # every result() has synchronised its stream
-        dt_e2e = time.perf_counter() - t0
-        e2e_total = depth * e2e_steps
-        extra_sims = [s_ for s_ in pipe.sims if s_ is not sim]
-        pipe.sims = []                        # `sim` is closed below, the others here
-        pipe.close()
-        for s_ in extra_sims:
-            s_.close()
-        e2e_how = (f"{depth} requests in flight (HostPipeline: {depth} handles, streams and host "
-                   f"threads, sb_tick_host), {e2e_steps} steps each; host clock around all of them")
-    else:
+        try:
+            dt_e2e, e2e_total, e2e_steps, e2e_how = _e2e_pipelined(
+                sim, depth, args, fields, L, multi, group, wl, ext)
+            e2e_done = True
+        except (MemoryError, _capi.SbError) as e:   # e.g. not enough page-locked memory
+            print(f"[bench] pipelined end-to-end leg unavailable ({e}); serial", file=sys.stderr)
+            depth = 1
+    if not e2e_done:
         host = [C.c_void_p(L.sb_host_alloc(nbytes)) for _ in range(3)]
         for hbuf, fld in zip(host, fields):
             sim._check(L.sb_download(sim._h, fld, hbuf))
