@@ -1,0 +1,367 @@
+// The reference's own unit tests, replayed in C++ through include/stroemung_b200.hpp (the
+// host-side mirror of the Rust API) against libstroemung_b200.so on a B200.
+//
+// Each test is named after the Rust test it restates and cites it.  Expected values are the
+// reference-held golden vectors of tests/golden/*.json (golden.inc is generated from them by
+// make_golden_inc.py); where the reference has no vector (grids beyond 4x3) the CPU oracle
+// (oracle/stroemung_oracle.h, test infrastructure) is the checker.  All floating-point
+// comparisons are on bit patterns, like `assert_eq!` and the insta snapshots.
+//
+//   test_reference_tests            run everything (needs a GPU; exit code = failed tests)
+//   test_reference_tests --list     print the test names, touch nothing (CPU check)
+//   test_reference_tests NAME...    run the named tests
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "stroemung_b200.hpp"
+#include "stroemung_oracle.h"
+
+#include "golden.inc"
+
+using namespace stroemung;
+
+// ---- a very small test harness --------------------------------------------------------
+struct Failure {
+    std::string what;
+};
+#define REQUIRE(cond)                                                                        \
+    do {                                                                                     \
+        if (!(cond))                                                                         \
+            throw Failure{std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " #cond}; \
+    } while (0)
+
+static std::vector<std::pair<std::string, std::function<void()>>> &registry() {
+    static std::vector<std::pair<std::string, std::function<void()>>> r;
+    return r;
+}
+struct Registrar {
+    Registrar(const char *name, std::function<void()> fn) { registry().emplace_back(name, fn); }
+};
+#define TEST(name)                                   \
+    static void name();                              \
+    static Registrar reg_##name(#name, name);        \
+    static void name()
+
+static bool same_bits(double a, double b) { return std::memcmp(&a, &b, sizeof a) == 0; }
+// residual norms are sums: the kernels add the reference's terms in a tree, so norms are held to
+// 1e-12 relative ("summation order beyond 2 terms is parity-unpinned")
+static bool close(double a, double b) {
+    return a == b || std::abs(a - b) <= 1e-12 * std::max(std::abs(a), std::abs(b));
+}
+static void require_bits(const GridArray<Real> &got, const double *want, const char *what) {
+    for (std::size_t i = 0; i < got.len(); ++i)
+        if (!same_bits(got.data()[i], want[i])) {
+            char buf[256];
+            std::snprintf(buf, sizeof buf, "%s[%zu]: got %a, want %a", what, i, got.data()[i], want[i]);
+            throw Failure{buf};
+        }
+}
+static View3x3 view(const double m[3][3]) {
+    View3x3 v;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) v[a][b] = m[a][b];
+    return v;
+}
+
+// ---- src/math.rs:192-402 (24 exact known-answer tests), evaluated on the device ---------
+TEST(math_test_du2dx) { // src/math.rs:197-240
+    for (const Kat1 &c : KAT_DU2DX) REQUIRE(same_bits(math::du2dx(view(c.a), c.d, c.gamma), c.expected));
+}
+TEST(math_test_dv2dy) { // src/math.rs:242-285
+    for (const Kat1 &c : KAT_DV2DY) REQUIRE(same_bits(math::dv2dy(view(c.a), c.d, c.gamma), c.expected));
+}
+TEST(math_test_duvdx) { // src/math.rs:287-324
+    for (const Kat2 &c : KAT_DUVDX)
+        REQUIRE(same_bits(math::duvdx(view(c.u), view(c.v), c.d, c.gamma), c.expected));
+}
+TEST(math_test_duvdy) { // src/math.rs:326-363
+    for (const Kat2 &c : KAT_DUVDY)
+        REQUIRE(same_bits(math::duvdy(view(c.u), view(c.v), c.d, c.gamma), c.expected));
+}
+TEST(math_test_laplacian) { // src/math.rs:365-402
+    for (const KatLap &c : KAT_LAPLACIAN)
+        REQUIRE(same_bits(math::laplacian(view(c.e), c.delx, c.dely), c.expected));
+}
+// ---- src/simulation.rs:449-569 (8 KATs) ------------------------------------------------------
+TEST(simulation_test_calculate_f) {
+    for (const KatFG &c : KAT_CALCULATE_F)
+        REQUIRE(same_bits(calculate_f(view(c.u), view(c.v), c.delx, c.dely, c.delt, c.gamma, c.reynolds),
+                          c.expected));
+}
+TEST(simulation_test_calculate_g) {
+    for (const KatFG &c : KAT_CALCULATE_G)
+        REQUIRE(same_bits(calculate_g(view(c.u), view(c.v), c.delx, c.dely, c.delt, c.gamma, c.reynolds),
+                          c.expected));
+}
+
+// ---- src/simulation.rs:571-618 `simulation_tick` ----------------------------------------------
+static UnfinalizedSimulation tick_case(GridSize size, UnfinalizedSimulationGrid grid) {
+    UnfinalizedSimulation u;
+    u.size = size;
+    u.cell_size = {0.1, 0.2};
+    u.delt = 0.005;
+    u.gamma = 0.9;
+    u.reynolds = 100.0;
+    u.sor_absolute_epsilon = 0.001;
+    u.max_iterations = 100;
+    u.initial_norm_squared = std::nullopt;
+    u.iterations = 0;
+    u.time = 0.0;
+    u.omega = 1.7;
+    u.grid = std::move(grid);
+    return u;
+}
+static void require_sim(const Simulation &sim, const SimSnap &want, const char *what) {
+    REQUIRE(sim.iterations() == want.iterations);
+    REQUIRE(same_bits(sim.time(), want.time));
+    REQUIRE(sim.initial_norm_squared().has_value());
+    REQUIRE(same_bits(*sim.initial_norm_squared(), want.initial_norm_squared));
+    require_bits(sim.grid.pressure(), want.p, what);
+    require_bits(sim.grid.u(), want.u, what);
+    require_bits(sim.grid.v(), want.v, what);
+}
+TEST(simulation_simulation_tick) {
+    const GridSize size{4, 3};
+    Simulation sim = Simulation::try_from(tick_case(size, presets::simple_inflow(size)));
+
+    auto [sor_iterations, norm_squared] = sim.run_simulation_tick();
+    require_bits(sim.f(), TICK_F_1, "f after tick 1");
+    require_bits(sim.g(), TICK_G_1, "g after tick 1");
+    require_bits(sim.rhs(), TICK_RHS_1, "rhs after tick 1");
+    require_sim(sim, TICK_SIM_1, "sim after tick 1");
+    REQUIRE(sor_iterations == TICK_ASSERT_ITERS[0]);          // assert_eq!(sor_iterations, 100)
+    REQUIRE(close(norm_squared, TICK_ASSERT_NORM[0]));        // 562901.7447199143
+
+    std::uint32_t last_sor_iterations = 0;
+    Real last_norm_squared = 0.0;
+    for (int i = 0; i < 100; ++i) std::tie(last_sor_iterations, last_norm_squared) = sim.run_simulation_tick();
+    REQUIRE(last_sor_iterations == TICK_ASSERT_ITERS[1]);     // 1
+    REQUIRE(close(last_norm_squared, TICK_ASSERT_NORM[1]));   // 3.8344148218167323e-20
+    require_bits(sim.f(), TICK_F_101, "f after tick 101");
+    require_bits(sim.g(), TICK_G_101, "g after tick 101");
+    require_bits(sim.rhs(), TICK_RHS_101, "rhs after tick 101");
+    require_sim(sim, TICK_SIM_101, "sim after tick 101");
+
+    for (int i = 0; i < 100; ++i) sim.run_simulation_tick();
+    require_sim(sim, TICK_SIM_201, "sim after tick 201");
+}
+
+// ---- src/simulation.rs:422-446 `serialize` -----------------------------------------------------
+TEST(simulation_serialize) {
+    const GridSize size{5, 7};
+    UnfinalizedSimulation u = tick_case(size, presets::empty(size));
+    u.cell_size = {1., 2.};
+    u.delt = 1.4;
+    u.gamma = 1.7;
+    Simulation simulation = Simulation::try_from(u);
+    const UnfinalizedSimulation out = simulation.to_unfinalized(); // what Serialize writes
+    REQUIRE(out.size == size);
+    REQUIRE(same_bits(out.delt, SERIALIZE_DELT));
+    REQUIRE(out.initial_norm_squared.has_value());
+    REQUIRE(same_bits(*out.initial_norm_squared, SERIALIZE_INITIAL_NORM));
+    REQUIRE(out.iterations == 0 && out.max_iterations == 100);
+    for (Real x : out.grid.pressure) REQUIRE(same_bits(x, 0.0));
+    for (Real x : out.grid.u) REQUIRE(same_bits(x, 0.0));
+    for (Real x : out.grid.v) REQUIRE(same_bits(x, 0.0));
+    for (const Cell &c : out.grid.cell_type) REQUIRE(c == Cell::Fluid());
+    REQUIRE(simulation.grid.boundaries().sorted_boundary_list.empty());
+    REQUIRE(simulation.grid.boundaries().fluid_cells == 35.0);
+}
+
+// ---- src/grid/mod.rs:683-706 `thin_boundary` ---------------------------------------------------
+static UnfinalizedSimulation grid_only(GridSize size, const std::vector<GridIndex> &noslip) {
+    UnfinalizedSimulationGrid g = presets::empty(size);
+    for (GridIndex idx : noslip) g.cell_type[idx] = Cell::Boundary(BoundaryCell::NoSlip());
+    UnfinalizedSimulation u = tick_case(size, std::move(g));
+    u.cell_size = {1., 1.};
+    return u;
+}
+TEST(grid_thin_boundary) {
+    const GridSize size{3, 3};
+    const std::vector<std::vector<GridIndex>> boundaries = {{{1, 0}, {1, 1}, {1, 2}},
+                                                            {{0, 1}, {1, 1}, {2, 1}}};
+    for (const auto &example : boundaries) {
+        bool is_err = false;
+        try {
+            Simulation::try_from(grid_only(size, example));
+        } catch (const BoundaryTooThinError &e) {
+            is_err = true;
+            REQUIRE(std::string(e.what()).find("BoundaryTooThinError") != std::string::npos);
+            // the first offender in x-major order is the one reported (:225-232)
+            REQUIRE(e.index == example[0]);
+            REQUIRE(e.kind == SB_KIND_NOSLIP);
+        }
+        REQUIRE(is_err);
+    }
+}
+
+// ---- src/grid/mod.rs:708-801 `rebuild_boundary_list` -------------------------------------------
+TEST(grid_rebuild_boundary_list) {
+    using K = EdgeType::Kind;
+    const GridSize size{3, 3};
+    struct Example {
+        std::vector<GridIndex> boundaries;
+        std::vector<std::optional<EdgeType>> neighbors;
+    };
+    auto some = [](K k, GridIndex cell) { return std::optional<EdgeType>(EdgeType::of(k, cell)); };
+    const std::vector<Example> examples = {
+        // Everything except for the middle cell is a boundary
+        {{{0, 0}, {0, 1}, {0, 2}, {1, 0}, {1, 2}, {2, 0}, {2, 1}, {2, 2}},
+         {std::nullopt, some(K::East, {0, 1}), std::nullopt, some(K::South, {1, 0}),
+          some(K::North, {1, 2}), std::nullopt, some(K::West, {2, 1}), std::nullopt}},
+        // All corners are boundaries
+        {{{0, 0}, {0, 2}, {2, 0}, {2, 2}},
+         {some(K::SouthEast, {0, 0}), some(K::NorthEast, {0, 2}), some(K::SouthWest, {2, 0}),
+          some(K::NorthWest, {2, 2})}},
+    };
+    // the neighbour indices the reference spells out (:727-764)
+    REQUIRE(examples[0].neighbors[1]->east_neighbor == GridIndex(1, 1));
+    REQUIRE(examples[0].neighbors[3]->south_neighbor == GridIndex(1, 1));
+    REQUIRE(examples[0].neighbors[4]->north_neighbor == GridIndex(1, 1));
+    REQUIRE(examples[0].neighbors[6]->west_neighbor == GridIndex(1, 1));
+    REQUIRE(examples[1].neighbors[0]->south_neighbor == GridIndex(0, 1));
+    REQUIRE(examples[1].neighbors[0]->east_neighbor == GridIndex(1, 0));
+    REQUIRE(examples[1].neighbors[3]->north_neighbor == GridIndex(2, 1));
+    REQUIRE(examples[1].neighbors[3]->west_neighbor == GridIndex(1, 2));
+
+    for (const Example &ex : examples) {
+        Simulation sim = Simulation::try_from(grid_only(size, ex.boundaries));
+        const BoundaryList bl = sim.grid.boundaries();
+        REQUIRE(bl.sorted_boundary_list.size() == ex.boundaries.size());
+        for (std::size_t i = 0; i < ex.boundaries.size(); ++i) {
+            REQUIRE(bl.sorted_boundary_list[i].first == ex.boundaries[i]);
+            REQUIRE(bl.sorted_boundary_list[i].second == ex.neighbors[i]);
+        }
+        REQUIRE(bl.fluid_cells == Real(9 - ex.boundaries.size()));
+    }
+}
+
+// ---- src/lib.rs:38-78 `draw_cells` + rebuild: edit, thin-wall roll-back -------------------------
+TEST(lib_draw_cells_rolls_back_thin_walls) {
+    const GridSize size{12, 10};
+    Simulation sim = Simulation::try_from(tick_case(size, presets::simple_inflow(size)));
+    const GridArray<Cell> before = sim.grid.cell_type();
+    REQUIRE(before(0, 3) == Cell::Boundary(BoundaryCell::Inflow({1.0, 0.0})));
+    // a 2x2 block in the open channel is a legal obstacle
+    REQUIRE(sim.grid.draw_cells(Cell::Boundary(BoundaryCell::NoSlip()), 5, 4));
+    GridArray<Cell> after = sim.grid.cell_type();
+    REQUIRE(after(5, 4) == Cell::Boundary(BoundaryCell::NoSlip()) && after(6, 5) == after(5, 4));
+    // painting fluid over one of its rows leaves a 1-cell wall with fluid on opposing
+    // sides: rebuild_boundary_list fails and the edit is rolled back
+    REQUIRE(!sim.grid.draw_cells(Cell::Fluid(), 5, 5));
+    REQUIRE(sim.grid.cell_type() == after);
+    sim.run_simulation_tick();
+}
+
+// ---- beyond the reference's fixtures: the default obstacle preset against the oracle ----------
+static void against_oracle(sb_sor_mode mode, int temporal_block, GridSize size, int ticks) {
+    UnfinalizedSimulation u = tick_case(size, presets::obstacle(size));
+    Extensions ext;
+    ext.sor_mode = mode;
+    ext.temporal_block = temporal_block;
+    Simulation sim = Simulation::try_from(u, ext);
+
+    std::vector<std::uint8_t> kind;
+    std::vector<sb_boundary_velocity> tab;
+    SimulationGrid::flatten(u.grid.cell_type, kind, tab);
+    std::vector<double> bu(kind.size(), 0.0), bv(kind.size(), 0.0);
+    for (const sb_boundary_velocity &t : tab) {
+        bu[t.x * size[1] + t.y] = t.u;
+        bv[t.x * size[1] + t.y] = t.v;
+    }
+    so_params op{};
+    op.nx = size[0];
+    op.ny = size[1];
+    op.delx = u.cell_size[0];
+    op.dely = u.cell_size[1];
+    op.delt = u.delt;
+    op.gamma = u.gamma;
+    op.reynolds = u.reynolds;
+    op.sor_absolute_epsilon = u.sor_absolute_epsilon;
+    op.omega = u.omega;
+    op.max_iterations = u.max_iterations;
+    op.sor_mode = mode == SB_SOR_RED_BLACK ? SO_SOR_RED_BLACK : SO_SOR_REFERENCE_ORDER;
+    so_sim *ref = nullptr;
+    std::uint64_t err[2];
+    REQUIRE(so_create(&op, nullptr, nullptr, nullptr, kind.data(), bu.data(), bv.data(), &ref, err) == SO_OK);
+    {
+        so_state st0;
+        so_get_state(ref, &st0);
+        REQUIRE(close(*sim.initial_norm_squared(), st0.initial_norm_squared));
+    }
+    for (int t = 0; t < ticks; ++t) {
+        std::uint32_t it = 0;
+        double norm = 0.0;
+        REQUIRE(so_tick(ref, &it, &norm) == SO_OK);
+        auto [git, gnorm] = sim.run_simulation_tick();
+        REQUIRE(git == it);
+        REQUIRE(close(gnorm, norm));
+        require_bits(sim.grid.pressure(), so_p(ref), "pressure");
+        require_bits(sim.grid.u(), so_u(ref), "u");
+        require_bits(sim.grid.v(), so_v(ref), "v");
+        require_bits(sim.f(), so_f(ref), "f");
+        require_bits(sim.g(), so_g(ref), "g");
+        require_bits(sim.rhs(), so_rhs(ref), "rhs");
+    }
+    so_state st;
+    so_get_state(ref, &st);
+    REQUIRE(same_bits(sim.grid.speed_range()[0], st.speed_range[0]));
+    REQUIRE(same_bits(sim.grid.speed_range()[1], st.speed_range[1]));
+    REQUIRE(same_bits(sim.grid.pressure_range()[0], st.pressure_range[0]));
+    REQUIRE(same_bits(sim.grid.pressure_range()[1], st.pressure_range[1]));
+    REQUIRE(sim.grid.boundaries().fluid_cells == st.fluid_cells);
+    so_destroy(ref);
+}
+TEST(obstacle_preset_reference_order_vs_oracle) { against_oracle(SB_SOR_REFERENCE_ORDER, 0, {100, 20}, 5); }
+TEST(obstacle_preset_red_black_vs_oracle) { against_oracle(SB_SOR_RED_BLACK, 0, {100, 20}, 5); }
+TEST(obstacle_channel_red_black_pass_kernels_vs_oracle) { against_oracle(SB_SOR_RED_BLACK, 4, {640, 300}, 2); }
+
+// ---- no CPU fallback: a construction that cannot reach a GPU is an error, not a slow answer ----
+TEST(invalid_arguments_are_errors) {
+    const GridSize size{4, 3};
+    UnfinalizedSimulation u = tick_case(size, presets::simple_inflow(size));
+    u.grid.pressure = GridArray<Real>::zeros({3, 3});
+    bool threw = false;
+    try {
+        Simulation::try_from(u);
+    } catch (const InvalidArgument &) {
+        threw = true;
+    }
+    REQUIRE(threw);
+}
+
+int main(int argc, char **argv) {
+    std::vector<std::string> only;
+    for (int i = 1; i < argc; ++i) {
+        if (!std::strcmp(argv[i], "--list")) {
+            for (auto &t : registry()) std::printf("%s\n", t.first.c_str());
+            std::printf("library: %s\n", sb_version());
+            return 0;
+        }
+        only.emplace_back(argv[i]);
+    }
+    int failed = 0, ran = 0;
+    for (auto &t : registry()) {
+        if (!only.empty() && std::find(only.begin(), only.end(), t.first) == only.end()) continue;
+        ++ran;
+        try {
+            t.second();
+            std::printf("ok      %s\n", t.first.c_str());
+        } catch (const Failure &f) {
+            ++failed;
+            std::printf("FAILED  %s: %s\n", t.first.c_str(), f.what.c_str());
+        } catch (const std::exception &e) {
+            ++failed;
+            std::printf("FAILED  %s: exception: %s\n", t.first.c_str(), e.what());
+        }
+        std::fflush(stdout);
+    }
+    std::printf("%d run, %d failed\n", ran, failed);
+    return failed ? 1 : (ran ? 0 : 2);
+}
