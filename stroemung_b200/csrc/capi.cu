@@ -511,7 +511,10 @@ sb_status sb_create(const sb_params *params, const double *p, const double *u, c
     if (velocities && n_velocities) s->velocities.assign(velocities, velocities + n_velocities);
     // a slab finishes construction collectively in sb_slab_connect
     if (!s->slab && (st = finish_create(s))) return fail(st);
-    SB_CUDA(cudaStreamSynchronize(s->stream));
+    if (cudaStreamSynchronize(s->stream) != cudaSuccess) {
+        set_error("sb_create: the construction kernels failed");
+        return fail(SB_CUDA_ERROR);
+    }
     *out = s;
     return SB_OK;
 }
@@ -522,6 +525,10 @@ sb_status sb_create_preset(const sb_params *params, int32_t preset, const double
     *out = nullptr;
     if (preset < 0 || preset > 5) {
         set_error("sb_create_preset: unknown preset");
+        return SB_INVALID_ARGUMENT;
+    }
+    if (n_args && !args) {
+        set_error("sb_create_preset: args is NULL");
         return SB_INVALID_ARGUMENT;
     }
     sb_sim *s = nullptr;
@@ -555,7 +562,10 @@ sb_status sb_create_preset(const sb_params *params, int32_t preset, const double
             s->velocities.push_back(sb_boundary_velocity{(uint64_t)x, 0, lid_u, 0.0});
     }
     if (!s->slab && (st = finish_create(s))) return fail(st);
-    SB_CUDA(cudaStreamSynchronize(s->stream));
+    if (cudaStreamSynchronize(s->stream) != cudaSuccess) {
+        set_error("sb_create: the construction kernels failed");
+        return fail(SB_CUDA_ERROR);
+    }
     *out = s;
     return SB_OK;
 }
