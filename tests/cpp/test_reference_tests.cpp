@@ -4,8 +4,8 @@
 // Each test is named after the Rust test it restates and cites it.  Expected values are the
 // reference-held golden vectors of tests/golden/*.json (golden.inc is generated from them by
 // make_golden_inc.py); where the reference has no vector (grids beyond 4x3) the CPU oracle
-// (oracle/stroemung_oracle.h, test infrastructure) is the checker.  All floating-point
-// comparisons are on bit patterns, like `assert_eq!` and the insta snapshots.
+// (oracle/stroemung_oracle.h, test infrastructure) is the checker.  Fields are compared on bit
+// patterns, like `assert_eq!` and the insta snapshots; residual norms within 1e-12 relative.
 //
 //   test_reference_tests            run everything (needs a GPU; exit code = failed tests)
 //   test_reference_tests --list     print the test names, touch nothing (CPU check)
@@ -321,6 +321,146 @@ static void against_oracle(sb_sor_mode mode, int temporal_block, GridSize size, 
 TEST(obstacle_preset_reference_order_vs_oracle) { against_oracle(SB_SOR_REFERENCE_ORDER, 0, {100, 20}, 5); }
 TEST(obstacle_preset_red_black_vs_oracle) { against_oracle(SB_SOR_RED_BLACK, 0, {100, 20}, 5); }
 TEST(obstacle_channel_red_black_pass_kernels_vs_oracle) { against_oracle(SB_SOR_RED_BLACK, 4, {640, 300}, 2); }
+
+// ---- the stage functions of the reference called one by one through the mirror --------------
+// (`run_simulation_tick` is exactly this sequence, src/simulation.rs:324-333)
+struct OracleTwin {
+    so_sim *ref = nullptr;
+    so_params op{};
+    OracleTwin(const UnfinalizedSimulation &u, sb_sor_mode mode) {
+        std::vector<std::uint8_t> kind;
+        std::vector<sb_boundary_velocity> tab;
+        SimulationGrid::flatten(u.grid.cell_type, kind, tab);
+        std::vector<double> bu(kind.size(), 0.0), bv(kind.size(), 0.0);
+        for (const sb_boundary_velocity &t : tab) {
+            bu[t.x * u.size[1] + t.y] = t.u;
+            bv[t.x * u.size[1] + t.y] = t.v;
+        }
+        op.nx = u.size[0];
+        op.ny = u.size[1];
+        op.delx = u.cell_size[0];
+        op.dely = u.cell_size[1];
+        op.delt = u.delt;
+        op.gamma = u.gamma;
+        op.reynolds = u.reynolds;
+        op.sor_absolute_epsilon = u.sor_absolute_epsilon;
+        op.omega = u.omega;
+        op.max_iterations = u.max_iterations;
+        op.sor_mode = mode == SB_SOR_RED_BLACK ? SO_SOR_RED_BLACK : SO_SOR_REFERENCE_ORDER;
+        std::uint64_t err[2];
+        if (so_create(&op, nullptr, nullptr, nullptr, kind.data(), bu.data(), bv.data(), &ref, err) != SO_OK)
+            throw Failure{"oracle: so_create failed"};
+    }
+    ~OracleTwin() { so_destroy(ref); }
+};
+static void require_fields(const Simulation &sim, so_sim *ref, const char *when) {
+    const std::string w(when);
+    require_bits(sim.grid.pressure(), so_p(ref), (w + ": pressure").c_str());
+    require_bits(sim.grid.u(), so_u(ref), (w + ": u").c_str());
+    require_bits(sim.grid.v(), so_v(ref), (w + ": v").c_str());
+    require_bits(sim.f(), so_f(ref), (w + ": f").c_str());
+    require_bits(sim.g(), so_g(ref), (w + ": g").c_str());
+    require_bits(sim.rhs(), so_rhs(ref), (w + ": rhs").c_str());
+}
+TEST(stage_functions_one_by_one_vs_oracle) {
+    const GridSize size{100, 20};
+    const UnfinalizedSimulation u = tick_case(size, presets::obstacle(size));
+    Simulation sim = Simulation::try_from(u);
+    OracleTwin o(u, SB_SOR_REFERENCE_ORDER);
+    require_fields(sim, o.ref, "after try_from");
+    for (int t = 0; t < 2; ++t) {
+        sim.grid.set_boundary_u_and_v();
+        REQUIRE(so_set_boundary_u_and_v(o.ref) == SO_OK);
+        require_fields(sim, o.ref, "after set_boundary_u_and_v");
+        sim.calculate_f_and_g();
+        so_calculate_f_and_g(o.ref);
+        sim.calculate_rhs();
+        so_calculate_rhs(o.ref);
+        require_fields(sim, o.ref, "after calculate_rhs");
+        REQUIRE(close(sim.calculate_norm_squared(), so_calculate_norm_squared(o.ref)));
+        std::uint32_t oit = 0;
+        double onorm = 0.0;
+        REQUIRE(so_solve_sor(o.ref, &oit, &onorm) == SO_OK);
+        auto [it, norm] = sim.solve_sor();
+        REQUIRE(it == oit);
+        REQUIRE(close(norm, onorm));
+        require_fields(sim, o.ref, "after solve_sor");
+        sim.set_u_and_v();
+        so_set_u_and_v(o.ref);
+        require_fields(sim, o.ref, "after set_u_and_v");
+        so_state st;
+        so_get_state(o.ref, &st);
+        REQUIRE(same_bits(sim.grid.speed_range()[1], st.speed_range[1]));
+        REQUIRE(same_bits(sim.grid.pressure_range()[0], st.pressure_range[0]));
+        REQUIRE(same_bits(sim.grid.pressure_range()[1], st.pressure_range[1]));
+    }
+    sim.grid.copy_pressure_to_boundaries();
+    REQUIRE(so_copy_pressure_to_boundaries(o.ref) == SO_OK);
+    require_fields(sim, o.ref, "after copy_pressure_to_boundaries");
+}
+
+// ---- pub scalar fields are writable (src/simulation.rs:50-69): the setters of the mirror -----
+TEST(pub_fields_written_through_the_mirror) {
+    const GridSize size{100, 20};
+    const UnfinalizedSimulation u = tick_case(size, presets::obstacle(size));
+    Simulation sim = Simulation::try_from(u);
+    OracleTwin o(u, SB_SOR_REFERENCE_ORDER);
+    sim.set_max_iterations(7);
+    sim.set_omega(1.5);
+    sim.set_delt(0.004);
+    o.op.max_iterations = 7;
+    o.op.omega = 1.5;
+    o.op.delt = 0.004;
+    so_state st;
+    so_get_state(o.ref, &st);
+    o.op.has_initial_norm = st.has_initial_norm;
+    o.op.initial_norm_squared = st.initial_norm_squared;
+    so_set_params(o.ref, &o.op);
+    REQUIRE(sim.max_iterations() == 7 && sim.omega() == 1.5 && sim.delt() == 0.004);
+    std::uint32_t oit = 0;
+    double onorm = 0.0;
+    REQUIRE(so_tick(o.ref, &oit, &onorm) == SO_OK);
+    auto [it, norm] = sim.run_simulation_tick();
+    REQUIRE(it == 7 && oit == 7);   // the obstacle preset always runs into the cap
+    REQUIRE(close(norm, onorm));
+    require_fields(sim, o.ref, "after a tick with edited parameters");
+    REQUIRE(same_bits(sim.time(), 0.004));
+    // initial_norm_squared = None: solve_sor latches the norm after its first sweep (:229-237)
+    sim.set_initial_norm_squared(std::nullopt);
+    so_clear_initial_norm(o.ref);
+    REQUIRE(!sim.initial_norm_squared().has_value());
+    REQUIRE(so_tick(o.ref, &oit, &onorm) == SO_OK);
+    std::tie(it, norm) = sim.run_simulation_tick();
+    REQUIRE(it == oit && close(norm, onorm));
+    so_get_state(o.ref, &st);
+    REQUIRE(sim.initial_norm_squared().has_value());
+    REQUIRE(close(*sim.initial_norm_squared(), st.initial_norm_squared));
+    require_fields(sim, o.ref, "after the latching tick");
+    REQUIRE(sim.iterations() == 2);
+}
+
+// ---- device-side mask generation equals the host-side preset (src/grid/presets.rs:64-87) -----
+TEST(device_preset_equals_host_preset) {
+    const GridSize size{100, 20};
+    const UnfinalizedSimulation u = tick_case(size, presets::obstacle(size));
+    Simulation dev = Simulation::from_preset(u, /*obstacle*/ 2);
+    Simulation host = Simulation::try_from(u);
+    REQUIRE(dev.grid.cell_type() == host.grid.cell_type());
+    REQUIRE(dev.grid.cell_type() == u.grid.cell_type);
+    const BoundaryList a = dev.grid.boundaries(), b = host.grid.boundaries();
+    REQUIRE(a.fluid_cells == b.fluid_cells);
+    REQUIRE(a.sorted_boundary_list.size() == b.sorted_boundary_list.size());
+    for (std::size_t i = 0; i < a.sorted_boundary_list.size(); ++i)
+        REQUIRE(a.sorted_boundary_list[i] == b.sorted_boundary_list[i]);
+    auto [it_d, norm_d] = dev.run_ticks(3);      // src/lib.rs:214-219 ticks in a row
+    std::uint32_t it_h = 0;
+    Real norm_h = 0.0;
+    for (int t = 0; t < 3; ++t) std::tie(it_h, norm_h) = host.run_simulation_tick();
+    REQUIRE(it_d == it_h && close(norm_d, norm_h));
+    require_bits(dev.grid.pressure(), host.grid.pressure().data(), "pressure");
+    require_bits(dev.grid.u(), host.grid.u().data(), "u");
+    REQUIRE(dev.iterations() == 3 && host.iterations() == 3);
+}
 
 // ---- no CPU fallback: a construction that cannot reach a GPU is an error, not a slow answer ----
 TEST(invalid_arguments_are_errors) {

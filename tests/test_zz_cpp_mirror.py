@@ -23,7 +23,9 @@ NAMES = [
     "simulation_simulation_tick", "simulation_serialize", "grid_thin_boundary",
     "grid_rebuild_boundary_list", "lib_draw_cells_rolls_back_thin_walls",
     "obstacle_preset_reference_order_vs_oracle", "obstacle_preset_red_black_vs_oracle",
-    "obstacle_channel_red_black_pass_kernels_vs_oracle", "invalid_arguments_are_errors",
+    "obstacle_channel_red_black_pass_kernels_vs_oracle", "stage_functions_one_by_one_vs_oracle",
+    "pub_fields_written_through_the_mirror", "device_preset_equals_host_preset",
+    "invalid_arguments_are_errors",
 ]
 
 
