@@ -48,3 +48,33 @@ def test_no_cuda_device_fails_loudly():
     assert st == _capi.SB_CUDA_ERROR
     assert b"no CPU fallback" in _capi.lib().sb_last_error_string() or \
         b"cuda" in _capi.lib().sb_last_error_string().lower()
+
+
+def test_header_is_strict_c_and_field_offsets_match_the_bindings(tmp_path):
+    """The header compiles as C99 with -pedantic -Werror (it is the C ABI, not a C++ header),
+    and every field of the three structs sits at the offset the ctypes binding assumes --
+    measured by the C compiler, not derived by hand."""
+    import ctypes as C
+    import subprocess
+    structs = {"sb_params": _capi.Params, "sb_boundary_velocity": _capi.BoundaryVelocity,
+               "sb_state": _capi.State}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "stroemung_b200.h"',
+             'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror",
+                        f"-I{ROOT / 'include'}", str(src), "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True,
+                                                       text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
