@@ -11,10 +11,15 @@ Mirrors what serde derives for `UnfinalizedSimulation` / `UnfinalizedSimulationG
 Device-side the cell mask is a u8 kind (0 Fluid, 1 NoSlip, 2 Outflow, 3 Inflow,
 4 MovingWall [extension]) plus a sparse table of boundary velocities.
 
-Note: the reference parses with serde_json 1.0.140 without
-`float_roundtrip`; one fixture literal (-0.14603099243353101) is read 1 ulp low
-by it.  Python's parser is correctly rounded; `quirk_serde_json=True` reproduces
-the reference's value for that literal so golden snapshots can be matched.
+Note: the reference parses with serde_json 1.0.140 (Cargo.lock:526-527)
+without its `float_roundtrip` feature (Cargo.toml:18), whose number parser is fast but not
+correctly rounded: e.g. the fixture literal -0.14603099243353101 is read 1 ulp low.  Python's
+parser is correctly rounded.  `quirk_serde_json=True` parses numbers with `serde_json_f64`, a
+restatement of that crate's published algorithm (the crate itself is a dependency that is not
+vendored in /root/reference), so that a document loads to exactly the doubles the reference
+computes with; it is pinned by the value the reference's own snapshot holds for that literal
+(src/snapshots/stroemung__simulation__tests__deserialize-2.snap:42) and by
+`initial_norm_squared` 899.9547140394143 of the same test.
 """
 import json
 
@@ -22,9 +27,109 @@ import numpy as np
 
 KIND_FLUID, KIND_NOSLIP, KIND_OUTFLOW, KIND_INFLOW, KIND_MOVING_WALL = range(5)
 
-# literal -> double the reference's parser produced (pinned by
-# src/snapshots/stroemung__simulation__tests__deserialize-2.snap:42)
-_SERDE_QUIRKS = {"-0.14603099243353101": -0.146030992433531}
+# ---- serde_json 1.0.140, default features: how a JSON number becomes an f64 ----------------
+# src/de.rs of the crate: parse_integer / parse_decimal accumulate the digits into a u64
+# significand and stop taking digits once the next one would overflow it (digits of the integer
+# part that are dropped still count into the exponent, digits of the fraction are ignored);
+# parse_exponent adds the written exponent (saturating i32); f64_from_parts then computes
+# `significand as f64`, scaled by ONE multiplication or division by an exactly represented
+# power of ten (two roundings in all, where a correctly rounded parser has one), with a loop of
+# divisions by 1e308 for exponents below the table.
+_U64_MAX = (1 << 64) - 1
+_I32_MAX = (1 << 31) - 1
+_POW10 = [float(f"1e{i}") for i in range(309)]
+
+
+def _u64_overflows(significand, digit):
+    """the crate's overflow!(significand * 10 + digit, u64::MAX)"""
+    return significand >= _U64_MAX // 10 and (significand > _U64_MAX // 10
+                                              or digit > _U64_MAX % 10)
+
+
+def _f64_from_parts(positive, significand, exponent):
+    f = float(significand)          # `significand as f64`: round to nearest even
+    while True:
+        k = abs(exponent)
+        if k < len(_POW10):
+            if exponent >= 0:
+                f *= _POW10[k]
+                if f == float("inf"):
+                    raise ValueError("number out of range")
+            else:
+                f /= _POW10[k]
+            break
+        if f == 0.0:
+            break
+        if exponent >= 0:
+            raise ValueError("number out of range")
+        f /= 1e308
+        exponent += 308
+    return f if positive else -f
+
+
+def serde_json_f64(text):
+    """The f64 that serde_json 1.0.140 (no `float_roundtrip`, no `arbitrary_precision`)
+    deserialises the JSON number `text` to."""
+    s = text.strip()
+    i, n = 0, len(s)
+    positive = True
+    if i < n and s[i] == "-":
+        positive, i = False, i + 1
+    if i >= n or not s[i].isdigit():
+        raise ValueError(f"invalid number {text!r}")
+    significand, exponent = 0, 0
+    if s[i] == "0":                      # only one leading zero
+        i += 1
+        if i < n and s[i].isdigit():
+            raise ValueError(f"invalid number {text!r}")
+    else:
+        while i < n and s[i].isdigit():
+            d = ord(s[i]) - 48
+            if _u64_overflows(significand, d):
+                # parse_long_integer: the remaining integer digits only scale the value
+                while i < n and s[i].isdigit():
+                    exponent += 1
+                    i += 1
+                break
+            significand = significand * 10 + d
+            i += 1
+    if i < n and s[i] == ".":            # parse_decimal
+        i += 1
+        start = i
+        while i < n and s[i].isdigit():
+            d = ord(s[i]) - 48
+            if _u64_overflows(significand, d):
+                while i < n and s[i].isdigit():   # parse_decimal_overflow: digits ignored
+                    i += 1
+                break
+            significand = significand * 10 + d
+            exponent -= 1
+            i += 1
+        if i == start:
+            raise ValueError(f"invalid number {text!r}")
+    if i < n and s[i] in "eE":           # parse_exponent
+        i += 1
+        positive_exp = True
+        if i < n and s[i] in "+-":
+            positive_exp = s[i] == "+"
+            i += 1
+        if i >= n or not s[i].isdigit():
+            raise ValueError(f"invalid number {text!r}")
+        exp = 0
+        while i < n and s[i].isdigit():
+            d = ord(s[i]) - 48
+            if exp >= _I32_MAX // 10 and (exp > _I32_MAX // 10 or d > _I32_MAX % 10):
+                # parse_exponent_overflow: an error instead of +/- infinity, else +/- 0
+                if significand != 0 and positive_exp:
+                    raise ValueError("number out of range")
+                return 0.0 if positive else -0.0
+            exp = exp * 10 + d
+            i += 1
+        exponent = (min(exponent + exp, _I32_MAX) if positive_exp
+                    else max(exponent - exp, -_I32_MAX - 1))
+    if i != n:
+        raise ValueError(f"invalid number {text!r}")
+    return _f64_from_parts(positive, significand, exponent)
 
 
 def array_from_json(doc, dtype=np.float64):
@@ -110,10 +215,12 @@ def simulation_from_json(doc):
 
 
 def loads(text, quirk_serde_json=False):
-    """json.loads; optionally with the reference parser's 1-ulp quirk."""
+    """json.loads; optionally reading every float literal the way the reference's parser
+    does (`serde_json_f64`).  Integer literals stay Python ints: converted to f64 they are
+    rounded to nearest even by Python exactly as by Rust's `u64 as f64`."""
     if not quirk_serde_json:
         return json.loads(text)
-    return json.loads(text, parse_float=lambda s: _SERDE_QUIRKS.get(s, float(s)))
+    return json.loads(text, parse_float=serde_json_f64)
 
 
 def simulation_to_json(prm, grid):
