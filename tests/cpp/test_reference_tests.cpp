@@ -9,17 +9,21 @@
 //
 //   test_reference_tests            run everything (needs a GPU; exit code = failed tests)
 //   test_reference_tests --list     print the test names, touch nothing (CPU check)
+//   test_reference_tests --host     run the host_* tests only (file format; no device needed)
 //   test_reference_tests NAME...    run the named tests
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <memory>
+#include <sstream>
 #include <string>
 #include <tuple>
 #include <vector>
 
 #include "stroemung_b200.hpp"
+#include "stroemung_b200_json.hpp"
 #include "stroemung_oracle.h"
 
 #include "golden.inc"
@@ -462,6 +466,95 @@ TEST(device_preset_equals_host_preset) {
     REQUIRE(dev.iterations() == 3 && host.iterations() == 3);
 }
 
+// ---- the reference's file format (include/stroemung_b200_json.hpp); host_* tests need no GPU --
+static void require_parsed(const UnfinalizedSimulationGrid &g, const ParsedSnap &want, const char *what) {
+    REQUIRE(g.size == (GridSize{want.nx, want.ny}));
+    require_bits(g.pressure, want.p, what);
+    require_bits(g.u, want.u, what);
+    require_bits(g.v, want.v, what);
+    for (std::size_t i = 0; i < g.cell_type.len(); ++i) {
+        const Cell &c = g.cell_type.data()[i];
+        REQUIRE(c.kind_code() == want.kind[i]);
+        if (c.is_boundary() && c.boundary().has_velocity()) {
+            REQUIRE(same_bits(c.boundary().velocity[0], want.bu[i]));
+            REQUIRE(same_bits(c.boundary().velocity[1], want.bv[i]));
+        }
+    }
+}
+TEST(host_serde_json_number_parser) {
+    // the literal of src/test_data/small_simulation_with_boundaries.json that serde_json 1.0.140
+    // (no float_roundtrip) reads one ulp low; value from the reference's own snapshot
+    const double got = json::serde_json_f64("-0.14603099243353101");
+    REQUIRE(same_bits(got, SERDE_QUIRK_LITERAL_VALUE));
+    REQUIRE(!same_bits(got, std::strtod("-0.14603099243353101", nullptr)));
+    REQUIRE(same_bits(json::serde_json_f64("0.0"), 0.0) && same_bits(json::serde_json_f64("-0.0"), -0.0));
+    REQUIRE(json::serde_json_f64("1.5e3") == 1500.0 && json::serde_json_f64("2E+2") == 200.0);
+    REQUIRE(json::serde_json_f64("0.30000000000000004") == 0.30000000000000004);
+    REQUIRE(json::serde_json_f64("18446744073709551616") == 1844674407370955161.0 * 10.0);
+    REQUIRE(json::serde_json_f64("1e-400") == 0.0);
+    for (const char *bad : {"01", "1.", "-", "1e", ".5", "1e400", ""}) {
+        bool threw = false;
+        try {
+            json::serde_json_f64(bad);
+        } catch (const json::DeserializationError &) {
+            threw = true;
+        }
+        REQUIRE(threw);
+    }
+}
+TEST(host_deserialize_fixtures_like_the_reference) { // src/simulation.rs:409-420, src/grid/mod.rs:803-823
+    for (const ParsedSnap *f : {&FIXTURE_SMALL_SIMULATION, &FIXTURE_SIMPLE_SIMULATION}) {
+        std::istringstream reader(f->raw);
+        const UnfinalizedSimulation u = json::unfinalized_simulation_from_reader(reader);
+        REQUIRE(u.size == (GridSize{f->nx, f->ny}));
+        REQUIRE(!u.initial_norm_squared.has_value()); // the files do not carry it
+        REQUIRE(u.max_iterations == 100 && u.iterations == 0 && u.omega == 1.7);
+        require_parsed(u.grid, *f, "simulation fixture");
+    }
+    REQUIRE(json::unfinalized_simulation_from_reader(*std::make_unique<std::istringstream>(
+                FIXTURE_SMALL_SIMULATION.raw)).cell_size == (CellPhysicalSize{0.1, 0.2}));
+    for (const ParsedSnap *f : {&FIXTURE_SMALL_GRID, &FIXTURE_SIMPLE_GRID, &FIXTURE_NAST2D_GRID}) {
+        std::istringstream reader(f->raw);
+        require_parsed(json::unfinalized_grid_from_reader(reader), *f, "grid fixture");
+    }
+}
+TEST(host_serialize_round_trip) {
+    std::istringstream reader(FIXTURE_SMALL_SIMULATION.raw);
+    UnfinalizedSimulation u = json::unfinalized_simulation_from_reader(reader);
+    u.initial_norm_squared = 899.9547140394143;
+    u.time = 1.0050000000000006;
+    const std::string text = json::to_json(u);
+    REQUIRE(text.find("\"initial_norm_squared\":899.9547140394143,") != std::string::npos);
+    REQUIRE(text.find("{\"Boundary\":{\"Inflow\":{\"velocity\":[1.0,0.0]}}}") != std::string::npos);
+    REQUIRE(text.rfind("{\"size\":[4,3],\"cell_size\":[0.1,0.2],\"delt\":0.005,", 0) == 0);
+    const UnfinalizedSimulation back = json::simulation_from(json::parse(text));
+    REQUIRE(back.grid.pressure == u.grid.pressure && back.grid.u == u.grid.u && back.grid.v == u.grid.v);
+    REQUIRE(back.grid.cell_type == u.grid.cell_type);
+    REQUIRE(back.initial_norm_squared == u.initial_norm_squared && same_bits(back.time, u.time));
+    bool threw = false;
+    try {
+        json::parse("{\"size\": [4, 3]");
+    } catch (const json::DeserializationError &e) {
+        threw = std::string(e.what()).find("deserializing") != std::string::npos;
+    }
+    REQUIRE(threw);
+}
+// src/simulation.rs:409-420 `deserialize`: from_reader on the two fixture files, on the GPU
+TEST(simulation_deserialize) {
+    for (const ParsedSnap *f : {&FIXTURE_SIMPLE_SIMULATION, &FIXTURE_SMALL_SIMULATION}) {
+        std::istringstream reader(f->raw);
+        Simulation sim = simulation_from_reader(reader);
+        const double want = f == &FIXTURE_SMALL_SIMULATION ? FIXTURE_SMALL_SIMULATION_INITIAL_NORM
+                                                           : FIXTURE_SIMPLE_SIMULATION_INITIAL_NORM;
+        REQUIRE(sim.initial_norm_squared().has_value());
+        REQUIRE(close(*sim.initial_norm_squared(), want));   // 899.9547140394143 / 0.0
+        const UnfinalizedSimulation out = sim.to_unfinalized();
+        require_parsed(out.grid, *f, "state after from_reader");
+        const UnfinalizedSimulation again = json::simulation_from(json::parse(simulation_to_json(sim)));
+        REQUIRE(again.grid.pressure == out.grid.pressure && again.grid.cell_type == out.grid.cell_type);
+    }
+}
+
 // ---- no CPU fallback: a construction that cannot reach a GPU is an error, not a slow answer ----
 TEST(invalid_arguments_are_errors) {
     const GridSize size{4, 3};
@@ -479,6 +572,11 @@ TEST(invalid_arguments_are_errors) {
 int main(int argc, char **argv) {
     std::vector<std::string> only;
     for (int i = 1; i < argc; ++i) {
+        if (!std::strcmp(argv[i], "--host")) {
+            for (auto &t : registry())
+                if (t.first.rfind("host_", 0) == 0) only.push_back(t.first);
+            continue;
+        }
         if (!std::strcmp(argv[i], "--list")) {
             for (auto &t : registry()) std::printf("%s\n", t.first.c_str());
             std::printf("library: %s\n", sb_version());

@@ -25,8 +25,10 @@ NAMES = [
     "obstacle_preset_reference_order_vs_oracle", "obstacle_preset_red_black_vs_oracle",
     "obstacle_channel_red_black_pass_kernels_vs_oracle", "stage_functions_one_by_one_vs_oracle",
     "pub_fields_written_through_the_mirror", "device_preset_equals_host_preset",
-    "invalid_arguments_are_errors",
+    "host_serde_json_number_parser", "host_deserialize_fixtures_like_the_reference",
+    "host_serialize_round_trip", "simulation_deserialize", "invalid_arguments_are_errors",
 ]
+HOST_NAMES = [n for n in NAMES if n.startswith("host_")]   # file format only: no device needed
 
 
 @pytest.fixture(scope="module")
@@ -64,8 +66,18 @@ def test_cpp_mirror_has_no_cpu_fallback(binary):
     assert r.stdout.count("FAILED") == 2 and "ok " not in r.stdout
 
 
+@pytest.mark.parametrize("name", HOST_NAMES)
+def test_reference_file_format_through_the_cpp_mirror(binary, name):
+    """include/stroemung_b200_json.hpp: the reference's fixture files parse to the doubles and
+    cells its `deserialize` snapshots show (incl. serde_json's 1-ulp quirk), and what the mirror
+    serialises reads back identically -- host code, runs here on the CPU"""
+    r = run(binary, name)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert f"ok      {name}" in r.stdout
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("name", [n for n in NAMES if n not in HOST_NAMES])
 def test_reference_test_through_the_cpp_mirror(binary, name):
     r = run(binary, name)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
