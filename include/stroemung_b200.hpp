@@ -481,6 +481,17 @@ class Simulation {
         return {it, norm};
     }
 
+    /* one tick with HOST arrays authoritative (sb_tick_host): uploads p, u, v ([nx][ny] f64),
+     * ticks, downloads them into the outputs (which may alias the inputs), one synchronisation;
+     * include/stroemung_b200_pipeline.hpp keeps several such requests in flight */
+    std::pair<std::uint32_t, Real> tick_host(const Real *p_in, const Real *u_in, const Real *v_in,
+                                             Real *p_out, Real *u_out, Real *v_out) {
+        std::uint32_t it = 0;
+        Real norm = 0.0;
+        detail::check(sb_tick_host(h_, p_in, u_in, v_in, p_out, u_out, v_out, &it, &norm), h_);
+        return {it, norm};
+    }
+
     /* stage functions of the reference, in tick order */
     void calculate_f_and_g() { detail::check(sb_calculate_f_and_g(h_), h_); } /* :122-202 */
     void calculate_rhs() { detail::check(sb_calculate_rhs(h_), h_); }         /* :204-214 */

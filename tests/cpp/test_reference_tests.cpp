@@ -24,6 +24,7 @@
 
 #include "stroemung_b200.hpp"
 #include "stroemung_b200_json.hpp"
+#include "stroemung_b200_pipeline.hpp"
 #include "stroemung_oracle.h"
 
 #include "golden.inc"
@@ -553,6 +554,101 @@ TEST(simulation_deserialize) {
         const UnfinalizedSimulation again = json::simulation_from(json::parse(simulation_to_json(sim)));
         REQUIRE(again.grid.pressure == out.grid.pressure && again.grid.cell_type == out.grid.cell_type);
     }
+}
+
+// ---- ticks on HOST arrays, several in flight (include/stroemung_b200_pipeline.hpp) ------------
+// five independent states through a pipeline of three handles, four ticks each, on pinned
+// buffers: every request ends on the oracle's bits whatever handle served which step
+TEST(pipeline_three_requests_in_flight) {
+    const GridSize size{330, 420}; // large enough for the pass kernels
+    const std::size_t n = size[0] * size[1];
+    UnfinalizedSimulation base = tick_case(size, presets::obstacle(size));
+    // the residual norm a solve has to beat is latched state of a HANDLE
+    // (src/simulation.rs:229-237): every handle and every oracle gets the same one
+    base.initial_norm_squared = 2.5e-3;
+    base.max_iterations = 40; // ten passes of four sweeps per tick
+    Extensions ext;
+    ext.sor_mode = SB_SOR_RED_BLACK;
+    HostPipeline pipe(3, [&] { return Simulation::try_from(base, ext); });
+    REQUIRE(pipe.depth() == 3 && pipe.field_len() == n);
+
+    std::vector<std::uint8_t> kind;
+    std::vector<sb_boundary_velocity> tab;
+    SimulationGrid::flatten(base.grid.cell_type, kind, tab);
+    std::vector<double> bu(n, 0.0), bv(n, 0.0);
+    for (const sb_boundary_velocity &t : tab) {
+        bu[t.x * size[1] + t.y] = t.u;
+        bv[t.x * size[1] + t.y] = t.v;
+    }
+    const int requests = 5, ticks = 4;
+    std::vector<PinnedField> fields; // p, u, v of request r at 3 r, 3 r + 1, 3 r + 2
+    std::vector<so_sim *> oracles;
+    std::uint64_t rng = 0x5EED5EEDull;
+    auto uniform = [&rng] { // splitmix64 -> [-1, 1)
+        rng += 0x9E3779B97F4A7C15ull;
+        std::uint64_t z = rng;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        return static_cast<double>(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+    };
+    for (int r = 0; r < requests; ++r) {
+        for (int k = 0; k < 3; ++k) {
+            fields.emplace_back(n);
+            for (std::size_t i = 0; i < n; ++i) fields.back()[i] = (k == 0 ? 1.0 : 0.05) * uniform();
+        }
+        so_params op{};
+        op.nx = size[0];
+        op.ny = size[1];
+        op.delx = base.cell_size[0];
+        op.dely = base.cell_size[1];
+        op.delt = base.delt;
+        op.gamma = base.gamma;
+        op.reynolds = base.reynolds;
+        op.sor_absolute_epsilon = base.sor_absolute_epsilon;
+        op.omega = base.omega;
+        op.max_iterations = base.max_iterations;
+        op.has_initial_norm = 1;
+        op.initial_norm_squared = 2.5e-3;
+        op.sor_mode = SO_SOR_RED_BLACK;
+        so_sim *o = nullptr;
+        std::uint64_t err[2];
+        REQUIRE(so_create(&op, fields[3 * r].data(), fields[3 * r + 1].data(), fields[3 * r + 2].data(),
+                          kind.data(), bu.data(), bv.data(), &o, err) == SO_OK);
+        oracles.push_back(o);
+    }
+    std::vector<std::vector<HostPipeline::Result>> results(requests);
+    for (int t = 0; t < ticks; ++t) {
+        std::vector<std::future<HostPipeline::Result>> futs; // 5 requests queued on 3 handles
+        for (int r = 0; r < requests; ++r)
+            futs.push_back(pipe.submit(fields[3 * r].data(), fields[3 * r + 1].data(), fields[3 * r + 2].data()));
+        for (int r = 0; r < requests; ++r) results[r].push_back(futs[r].get());
+    }
+    for (int r = 0; r < requests; ++r) {
+        for (int t = 0; t < ticks; ++t) {
+            std::uint32_t oit = 0;
+            double onorm = 0.0;
+            REQUIRE(so_tick(oracles[r], &oit, &onorm) == SO_OK);
+            REQUIRE(results[r][t].first == oit);
+            REQUIRE(close(results[r][t].second, onorm));
+        }
+        for (std::size_t i = 0; i < n; ++i) {
+            REQUIRE(same_bits(fields[3 * r][i], so_p(oracles[r])[i]));
+            REQUIRE(same_bits(fields[3 * r + 1][i], so_u(oracles[r])[i]));
+            REQUIRE(same_bits(fields[3 * r + 2][i], so_v(oracles[r])[i]));
+        }
+        so_destroy(oracles[r]);
+    }
+    // a failing request surfaces through its future, the pipeline keeps serving
+    bool threw = false;
+    try {
+        pipe.submit(nullptr, nullptr, nullptr).get();
+    } catch (const SimulationError &) {
+        threw = true;
+    }
+    REQUIRE(threw);
+    REQUIRE(pipe.submit(fields[0].data(), fields[1].data(), fields[2].data()).get().first > 0);
+    pipe.close();
 }
 
 // ---- no CPU fallback: a construction that cannot reach a GPU is an error, not a slow answer ----
