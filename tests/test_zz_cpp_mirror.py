@@ -8,6 +8,7 @@ CPU oracle.  Here: build it, check it on the CPU as far as that goes, run every 
 (The file sorts last so a harness problem cannot mask the parity tests under `pytest -x`.)
 """
 import subprocess
+import sys
 from pathlib import Path
 
 import pytest
@@ -36,7 +37,8 @@ HOST_NAMES = [n for n in NAMES if n.startswith("host_")]   # file format only: n
 def binary():
     # the product library and the oracle are prebuilt (__graft_entry__.build()); only the test
     # binary is (re)made here -- a few seconds of g++, also on the GPU box
-    r = subprocess.run(["make", "-C", str(CPP)], capture_output=True, text=True, timeout=900)
+    r = subprocess.run(["make", "-C", str(CPP), f"PYTHON={sys.executable}"], capture_output=True,
+                       text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert BIN.exists()
     return BIN
