@@ -78,3 +78,53 @@ def test_header_is_strict_c_and_field_offsets_match_the_bindings(tmp_path):
         assert int(got[cname]) == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_plain_c_host_links_and_fails_loudly_without_a_device(tmp_path):
+    """A C99 host (no C++ runtime of its own, no Python) links against the library by name and
+    drives the construction entry point: without a CUDA device it gets SB_CUDA_ERROR and the
+    "no CPU fallback" message; with one it constructs and ticks the 4x3 case of the reference's
+    `simulation_tick` test (src/simulation.rs:571-594) and must see 100 SOR iterations."""
+    import subprocess
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "stroemung_b200.h"
+int main(void) {
+    sb_params p;
+    unsigned char kind[12] = {1, 3, 1,  1, 0, 1,  1, 0, 1,  1, 2, 1};   /* simple_inflow([4, 3]) */
+    sb_boundary_velocity inflow = {0, 1, 1.0, 0.0};
+    sb_sim *sim = NULL;
+    uint32_t it = 0;
+    double norm = 0.0;
+    sb_status st;
+    memset(&p, 0, sizeof p);
+    p.nx = 4; p.ny = 3; p.delx = 0.1; p.dely = 0.2; p.delt = 0.005; p.gamma = 0.9;
+    p.reynolds = 100.0; p.sor_absolute_epsilon = 0.001; p.omega = 1.7; p.max_iterations = 100;
+    p.sor_mode = SB_SOR_REFERENCE_ORDER; p.device = -1;
+    st = sb_create(&p, NULL, NULL, NULL, kind, &inflow, 1, &sim);
+    if (st != SB_OK) {
+        printf("status %d: %s\n", (int)st, sb_last_error_string());
+        return sim == NULL ? 10 + (int)st : 99;
+    }
+    st = sb_tick(sim, &it, &norm);
+    printf("tick status %d iterations %u norm %.17g\n", (int)st, (unsigned)it, norm);
+    sb_destroy(sim);
+    return st == SB_OK && it == 100 ? 0 : 1;
+}
+''')
+    exe = tmp_path / "host"
+    lib_dir = ROOT / "stroemung_b200"
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror",
+                        f"-I{ROOT / 'include'}", str(src), "-o", str(exe), f"-L{lib_dir}",
+                        "-lstroemung_b200", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    from tests.conftest import _cuda_device_count
+    if _cuda_device_count() == 0:
+        assert r.returncode == 10 + _capi.SB_CUDA_ERROR, (r.returncode, r.stdout)
+        assert "no CPU fallback" in r.stdout or "cuda" in r.stdout.lower()
+    else:
+        assert r.returncode == 0, r.stdout
+        assert "iterations 100 norm 562901.74471991" in r.stdout

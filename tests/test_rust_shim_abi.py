@@ -102,3 +102,30 @@ def test_enum_constants_match_the_header():
         m = re.search(r"\b" + name + r"\s*=\s*(\d+)", HEADER) or \
             re.search(r"#define " + name + r"\s+(\d+)", HEADER)
         assert m and int(m.group(1)) == int(value), name
+
+
+def test_shim_delimiters_balance_and_items_are_well_formed():
+    """the cheapest stand-in for a compiler: after stripping comments, strings and char
+    literals every (, [ and { closes in order; every `fn` has a body or a `;`"""
+    text = re.sub(r"//[^\n]*", "", SHIM)
+    text = re.sub(r'"(?:\\.|[^"\\])*"', '""', text)
+    text = re.sub(r"b?'(?:\\.|[^'\\])'", "' '", text)
+    pairs = {")": "(", "]": "[", "}": "{"}
+    stack = []
+    for i, ch in enumerate(text):
+        if ch in "([{":
+            stack.append((ch, i))
+        elif ch in pairs:
+            assert stack and stack[-1][0] == pairs[ch], (ch, text[max(0, i - 80):i + 20])
+            stack.pop()
+    assert not stack, stack[-1]
+    for m in re.finditer(r"\bfn\s+\w+\s*\(", text):
+        depth, j = 0, m.end() - 1
+        while True:
+            depth += text[j] == "("
+            depth -= text[j] == ")"
+            j += 1
+            if depth == 0:
+                break
+        tail = text[j:j + 200]
+        assert re.match(r"\s*(->\s*[^;{]+)?\s*[;{]", tail), tail[:80]
