@@ -1,5 +1,10 @@
 //! `src/gpu.rs` -- the reference-side binding of libstroemung_b200.so (include/stroemung_b200.h).
 //!
+//! Besides adding this file, ONE change to existing code is needed: the five fields of
+//! `UnfinalizedSimulationGrid` (src/grid/mod.rs:86-91: `size`, `pressure`, `u`, `v`, `cell_type`)
+//! are private to `grid`; make them `pub(crate)` so that `try_from_with` below can hand the
+//! arrays to the GPU without going through the CPU `SimulationGrid::try_from` first.
+//!
 //! A maintainer of wickedchicken/stroemung adds this file (plus `mod gpu;` in `src/lib.rs` and
 //! the `build.rs` next to it) to run `Simulation::run_simulation_tick` and everything it calls
 //! (src/simulation.rs:324-333) on a B200.  **Source only**: the image this library is built in has
