@@ -359,7 +359,9 @@ def _e2e_pipelined(sim, depth, args, fields, L, multi, group, wl, ext):
     for bufs in req:
         for hbuf, fld in zip(bufs, fields):
             sim._check(L.sb_download(sim._h, fld, hbuf))
-    e2e_steps = max(2, min(args.steps, 4))
+    # enough steps per request for the requests to fall out of lockstep and for the fill (first
+    # uploads with nothing to overlap) and drain (last downloads) to amortise
+    e2e_steps = max(2, min(args.steps, 10))
     for bufs in req:                      # one untimed step per request (first-touch)
         pipe.submit(*bufs).result()
 
