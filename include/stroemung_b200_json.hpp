@@ -24,6 +24,7 @@
 #include <charconv>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <istream>
 #include <iterator>
 #include <limits>
@@ -445,6 +446,49 @@ inline std::string to_json(const UnfinalizedSimulation &u) { /* field order of s
 }
 
 } // namespace json
+
+/* ---- NaSt2D `.out` binaries (what the reference's converter reads,
+ * python/generate_test_data.py:107-162): two C ints imax, jmax; then U, V, P, T as
+ * (imax+2)*(jmax+2) C doubles each, x-major; then the flag field as C ints (bit 0x10 = fluid).
+ * The converter's boundary-kind reconstruction (:46-78): a non-fluid cell of the left wall is
+ * Inflow carrying the file's (u, v), of the right wall Outflow, everything else NoSlip. ------- */
+namespace nast2d {
+inline UnfinalizedSimulationGrid grid_from_out(const std::string &bytes) {
+    auto need = [&](std::size_t n) {
+        if (bytes.size() < n) throw json::DeserializationError("NaSt2D .out file is truncated");
+    };
+    auto int_at = [&](std::size_t off) {
+        std::int32_t v;
+        std::memcpy(&v, bytes.data() + off, 4); /* little-endian C int, like the converter's default */
+        return v;
+    };
+    need(8);
+    const std::int32_t imax = int_at(0), jmax = int_at(4);
+    if (imax < 0 || jmax < 0) throw json::DeserializationError("NaSt2D .out file: negative size");
+    const GridSize size{static_cast<std::size_t>(imax) + 2, static_cast<std::size_t>(jmax) + 2};
+    const std::size_t n = size[0] * size[1];
+    need(8 + 4 * n * 8 + n * 4);
+    UnfinalizedSimulationGrid g;
+    g.size = size;
+    GridArray<Real> *fields[3] = {&g.u, &g.v, &g.pressure}; /* file order U, V, P, (T) */
+    for (int f = 0; f < 3; ++f) {
+        *fields[f] = GridArray<Real>(size);
+        std::memcpy(fields[f]->data(), bytes.data() + 8 + static_cast<std::size_t>(f) * n * 8, n * 8);
+    }
+    const std::size_t flags = 8 + 4 * n * 8;
+    g.cell_type = GridArray<Cell>(size, Cell::Boundary(BoundaryCell::NoSlip()));
+    auto fluid = [&](std::size_t x, std::size_t y) { return (int_at(flags + (x * size[1] + y) * 4) & 0x10) != 0; };
+    for (std::size_t x = 0; x < size[0]; ++x)
+        for (std::size_t y = 0; y < size[1]; ++y)
+            if (fluid(x, y)) g.cell_type(x, y) = Cell::Fluid();
+    for (std::size_t y = 1; y + 1 < size[1]; ++y) {
+        if (!fluid(0, y)) g.cell_type(0, y) = Cell::Boundary(BoundaryCell::Inflow({g.u(0, y), g.v(0, y)}));
+        if (!fluid(size[0] - 1, y)) g.cell_type(size[0] - 1, y) = Cell::Boundary(BoundaryCell::Outflow());
+    }
+    return g;
+}
+inline UnfinalizedSimulationGrid grid_from_reader(std::istream &reader) { return grid_from_out(json::slurp(reader)); }
+} // namespace nast2d
 
 /* Simulation::from_reader (src/simulation.rs:117-120): deserialise, then try_from */
 inline Simulation simulation_from_reader(std::istream &reader, const Extensions &ext = {}) {

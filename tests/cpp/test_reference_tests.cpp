@@ -519,6 +519,34 @@ TEST(host_deserialize_fixtures_like_the_reference) { // src/simulation.rs:409-42
         require_parsed(json::unfinalized_grid_from_reader(reader), *f, "grid fixture");
     }
 }
+// python/test_generate_test_data.py:28-49: the NaSt2D .out fixture through the converter
+TEST(host_nast2d_out_file_like_the_reference_converter) {
+    const std::string bytes(reinterpret_cast<const char *>(NAST2D_OUT), sizeof NAST2D_OUT);
+    const UnfinalizedSimulationGrid g = nast2d::grid_from_out(bytes);
+    require_parsed(g, NAST2D_EXPECTED, "small_data.out");
+    // ... and the JSON the reference keeps of the same state (tests/test_data/small_data.out.json)
+    // parses to the same grid -- except for the ONE pressure the reference's JSON parser reads
+    // an ulp low, p(2, 1) = -0.14603099243353101: the binary holds the exact double
+    std::istringstream reader(FIXTURE_NAST2D_GRID.raw);
+    const UnfinalizedSimulationGrid j = json::unfinalized_grid_from_reader(reader);
+    REQUIRE(j.u == g.u && j.v == g.v && j.cell_type == g.cell_type);
+    for (std::size_t x = 0; x < g.size[0]; ++x)
+        for (std::size_t y = 0; y < g.size[1]; ++y) {
+            if (x == 2 && y == 1) {
+                REQUIRE(g.pressure(x, y) == std::strtod("-0.14603099243353101", nullptr));
+                REQUIRE(same_bits(j.pressure(x, y), SERDE_QUIRK_LITERAL_VALUE));
+            } else {
+                REQUIRE(same_bits(j.pressure(x, y), g.pressure(x, y)));
+            }
+        }
+    bool threw = false;
+    try {
+        nast2d::grid_from_out(bytes.substr(0, bytes.size() - 5));
+    } catch (const json::DeserializationError &) {
+        threw = true;
+    }
+    REQUIRE(threw);
+}
 TEST(host_serialize_round_trip) {
     std::istringstream reader(FIXTURE_SMALL_SIMULATION.raw);
     UnfinalizedSimulation u = json::unfinalized_simulation_from_reader(reader);

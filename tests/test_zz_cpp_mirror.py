@@ -27,7 +27,8 @@ NAMES = [
     "obstacle_channel_red_black_pass_kernels_vs_oracle", "stage_functions_one_by_one_vs_oracle",
     "pub_fields_written_through_the_mirror", "device_preset_equals_host_preset",
     "host_serde_json_number_parser", "host_deserialize_fixtures_like_the_reference",
-    "host_serialize_round_trip", "simulation_deserialize", "pipeline_three_requests_in_flight",
+    "host_nast2d_out_file_like_the_reference_converter", "host_serialize_round_trip",
+    "simulation_deserialize", "pipeline_three_requests_in_flight",
     "invalid_arguments_are_errors",
 ]
 HOST_NAMES = [n for n in NAMES if n.startswith("host_")]   # file format only: no device needed
